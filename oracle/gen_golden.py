@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on CPU (build container only),
+and pin oracle/sesr_oracle.py against every tensor the reference dumps.  TEST INFRASTRUCTURE ONLY.
+
+    python oracle/gen_golden.py            # all cases -> tests/golden/, writes ORACLE_PIN.json
+    python oracle/gen_golden.py --case x4_small --out /tmp/x.npz   (worker mode, scratch cwd)
+
+Each case runs in its own subprocess with a scratch cwd because the reference keeps all inter-op
+state in ./output_pt/**  and imports define.* by value (quan_func.py:11-14).
+"""
+import argparse
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, HERE)
+
+# name -> config
+CASES = {
+    # BASELINE.json config 1 (x4 runs on the 1-channel SR fixture, x2/NRDM on the DM one)
+    "x4_fixture":   dict(mflag=5, calib=4, calib_hw=(80, 960), inp="rand_SR_Input_80x960.pt", full=True),
+    "nrdm_fixture": dict(mflag=3, calib=3, calib_hw=(80, 960), inp="rand_DM_Input_80x960.pt", full=True),
+    "x2_fixture":   dict(mflag=6, calib=3, calib_hw=(80, 960), inp="rand_DM_Input_80x960.pt", full=True),
+    # small frames with every intermediate stored (thresholds from the same calibration runs)
+    "x4_small":     dict(mflag=5, calib=4, calib_hw=(80, 960), inp=(21, 37, 4321)),
+    "nrdm_small":   dict(mflag=3, calib=3, calib_hw=(80, 960), inp=(19, 45, 4322)),
+    "x2_small":     dict(mflag=6, calib=3, calib_hw=(80, 960), inp=(23, 34, 4323)),
+    # stress: positive-mean synthetic weights so the 18-bit per-PE clamp fires; PE_ADD_BIT=19 so the
+    # PE-sum clamp fires too (with 18/20 bits and 4 PEs it is arithmetically inert)
+    "synth_clamp":  dict(mflag=5, calib=2, calib_hw=(24, 40), inp=(20, 33, 99), synth_weights=7,
+                         pe_add_bit=19),
+    # stress: hand-set zero points on both sides of -128 (generic 9-bit operand path, rc != q1)
+    "synth_zero":   dict(mflag=6, calib=3, calib_hw=(80, 960), inp=(18, 41, 77),
+                         zeros=[-120, -131, -128, -100, -125, -110]),
+    # input with negative values -> calibrated z0 > -128
+    "synth_neg":    dict(mflag=3, calib=2, calib_hw=(24, 40), inp=(17, 29, 55), signed_input=True),
+}
+CIN = {3: 3, 5: 1, 6: 3}
+RSH = {3: 1, 5: 4, 6: 2}
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def make_input(cfg, torch):
+    if isinstance(cfg["inp"], str):
+        import ref_harness as rh
+        return torch.load(os.path.join(rh.REF, cfg["inp"]), map_location="cpu").float()
+    h, w, seed = cfg["inp"]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(1, CIN[cfg["mflag"]], h, w, generator=g)
+    if cfg.get("signed_input"):
+        x = x * 2 - 1
+    return x
+
+
+def synth_override(model, seed, torch):
+    """Replace the collapsed conv weights with positive-mean synthetic ones (clamp stress)."""
+    g = torch.Generator().manual_seed(seed)
+    convs = [model.conv_first.conv_expand] + [b.conv_expand for b in model.residual_block] + [model.conv_last.conv_expand]
+    for c in convs:
+        w = torch.rand(c.weight.shape, generator=g) * 1.2 - 0.55
+        b = torch.rand(c.bias.shape, generator=g) * 4 - 2
+        c.weight = torch.nn.Parameter(w * 0.02)
+        c.bias = torch.nn.Parameter(b)
+
+
+def worker(name, out):
+    import torch
+    import ref_harness as rh
+    import sesr_oracle as orc
+    torch.set_grad_enabled(False)
+    cfg = CASES[name]
+    mflag = cfg["mflag"]
+    ns = rh.import_reference(mflag, dumps=True)
+    if "pe_add_bit" in cfg:
+        ns.define.PE_ADD_BIT = cfg["pe_add_bit"]
+    pe_add_bit = ns.define.PE_ADD_BIT
+
+    def build(sim):
+        m = rh.build_float_model(ns, mflag, sim=sim)
+        if "synth_weights" in cfg:
+            synth_override(m, cfg["synth_weights"], torch)
+        return m
+
+    # ---- calibration (test.py path, exe_mode 0) ----
+    g0 = rh.quantize_graph(ns, build(sim=False), 0)
+    rh.reset_minmax()
+    gen = torch.Generator().manual_seed(1234)
+    h, w = cfg["calib_hw"]
+    fq_first = None
+    for i in range(cfg["calib"]):
+        xc = torch.rand(1, CIN[mflag], h, w, generator=gen)
+        if cfg.get("signed_input"):
+            xc = xc * 2 - 1
+        yc = g0(xc)
+        if i == 0:
+            fq_first = (xc.numpy().copy(), yc.numpy().copy())
+    scales, zeros, mins, maxs = rh.calibration_tail(ns)
+    if "zeros" in cfg:
+        zeros = list(cfg["zeros"])
+        rh.write_thresholds(scales, zeros)
+
+    # ---- integer sim (sim.py path, exe_mode 1) ----
+    msim = build(sim=True)
+    convs = [msim.conv_first.conv_expand] + [b.conv_expand for b in msim.residual_block] + [msim.conv_last.conv_expand]
+    wf = [c.weight.detach().numpy().copy() for c in convs]
+    bf = [c.bias.detach().numpy().copy() for c in convs]
+    g1 = rh.quantize_graph(ns, msim, 1)
+    x = make_input(cfg, torch)
+    yout = g1(x).numpy()
+
+    def ld(p):
+        v = torch.load(p, map_location="cpu")
+        return v.numpy() if hasattr(v, "numpy") else v
+
+    ref = {}
+    for i in range(6):
+        ref["q%d" % i] = ld("output_pt/input/input.%d.pt" % i)
+    for i in range(5):
+        ref["pe_add%d" % i] = ld("output_pt/pe_add/pe_add_output%d.pt" % i)
+        for p in range(4):
+            ref["pe%d_%d" % (i, p)] = ld("output_pt/pe_out/pe_output%d_%d.pt" % (i, p))
+        ref["W%d" % i] = ld("output_pt/weight/conv.weight.%d.pt" % i)
+        ref["sw%d" % i] = ld("output_pt/weight/conv.weight.%d.scale.pt" % i)
+        ref["K%d" % i] = ld("output_pt/bias/conv.bias.quan%d.pt" % i).reshape(-1)
+    ref["shortcut"] = ld("output_pt/residual/shortcut_tensor.pt")
+    tags = ["0_1", "1_2", "2_3", "3_4", "4_5", "res"]
+    Ms = [int(ld("output_pt/requan_factor/requan_%s.pt" % t)) for t in tags]
+    Ns = [int(ld("output_pt/requan_factor/n_%s.pt" % t)) for t in tags]
+
+    # ---- pin the oracle against the reference dumps (bit-for-bit) ----
+    net = orc.derive_net(wf, bf, scales, zeros, RSH[mflag], pe_add_bit=pe_add_bit)
+    trace = {}
+    q5, y = orc.forward_int(net, x.numpy(), trace=trace)
+    checks = {}
+
+    def eq(key, a, b):
+        a = np.asarray(a, dtype=np.float64).reshape(-1)
+        b = np.asarray(b, dtype=np.float64).reshape(-1)
+        ok = a.shape == b.shape and bool(np.array_equal(a, b))
+        checks[key] = ok
+        if not ok:
+            nbad = int((a != b).sum()) if a.shape == b.shape else -1
+            print("MISMATCH %s/%s: %d elements" % (name, key, nbad), file=sys.stderr)
+
+    for i in range(5):
+        eq("W%d" % i, net.layers[i].W, ref["W%d" % i])
+        checks["sw%d" % i] = (net.layers[i].sw == ref["sw%d" % i])
+        eq("K%d" % i, net.layers[i].K, ref["K%d" % i])
+        eq("pe_add%d" % i, trace["pe_add%d" % i], ref["pe_add%d" % i])
+        for p in range(4):
+            eq("pe%d_%d" % (i, p), trace["pe%d_%d" % (i, p)], ref["pe%d_%d" % (i, p)])
+    for i in range(6):
+        eq("q%d" % i, trace["q%d" % i], ref["q%d" % i])
+    eq("shortcut", trace["shortcut"], ref["shortcut"])
+    eq("yout", y, yout)
+    checks["M"] = ([l.M for l in net.layers] + [net.Mr] == Ms)
+    checks["n"] = ([l.n for l in net.layers] + [net.nr] == Ns)
+    sc2, zr2 = orc.minmax_to_thresholds(mins, maxs)
+    checks["tail_scales"] = (sc2 == [float(s) for s in scales])
+    if "zeros" not in cfg:
+        checks["tail_zeros"] = (zr2 == [int(z) for z in zeros])
+
+    # clamp activity (informational)
+    act = {}
+    for i in range(5):
+        raw = sum(trace["pe%d_%d" % (i, p)].astype(np.int64) for p in range(4))
+        act["clamp18_hits_L%d" % i] = int(sum(((trace["pe%d_%d" % (i, p)] == 2 ** 17 - 1) | (trace["pe%d_%d" % (i, p)] == -2 ** 17)).sum() for p in range(4)))
+        act["clampadd_hits_L%d" % i] = int((raw != trace["pe_add%d" % i]).sum())
+        act["K_sat_L%d" % i] = int(((net.layers[i].K == 32767) | (net.layers[i].K == -32768)).sum())
+
+    # ---- store ----
+    d = dict(x=x.numpy().astype(np.float32), scales=np.array(scales, dtype=np.float64),
+             zeros=np.array(zeros, dtype=np.int64), mins=np.array(mins, dtype=np.float64),
+             maxs=np.array(maxs, dtype=np.float64), M=np.array(Ms, dtype=np.int64),
+             n=np.array(Ns, dtype=np.int64), r=np.int64(RSH[mflag]), mflag=np.int64(mflag),
+             pe_add_bit=np.int64(pe_add_bit), calib_n=np.int64(cfg["calib"]),
+             calib_hw=np.array(cfg["calib_hw"], dtype=np.int64),
+             signed_input=np.int64(1 if cfg.get("signed_input") else 0))
+    for i in range(5):
+        d["wf%d" % i] = wf[i].astype(np.float32)
+        d["bf%d" % i] = bf[i].astype(np.float32)
+        d["W%d" % i] = ref["W%d" % i].astype(np.int8)
+        d["sw%d" % i] = np.float64(ref["sw%d" % i])
+        d["K%d" % i] = ref["K%d" % i].astype(np.int32)
+    d["q5"] = ref["q5"].astype(np.int8)
+    hashes = {}
+    for i in range(5):
+        hashes["q%d" % i] = sha(ref["q%d" % i].astype(np.int8))
+        hashes["pe_add%d" % i] = sha(ref["pe_add%d" % i].astype(np.int32))
+    hashes["q5"] = sha(ref["q5"].astype(np.int8))
+    hashes["yout"] = sha(yout.astype(np.float32))
+    if not cfg.get("full"):
+        for i in range(5):
+            d["q%d" % i] = ref["q%d" % i].astype(np.int8)
+            d["pe_add%d" % i] = ref["pe_add%d" % i].astype(np.int32)
+            for p in range(4):
+                d["pe%d_%d" % (i, p)] = ref["pe%d_%d" % (i, p)].astype(np.int32)
+        d["shortcut"] = ref["shortcut"].astype(np.float32)
+        d["yout"] = yout.astype(np.float32)
+        # mode-0 (fake-quant, test.py path) golden on the same small input: one fresh frame
+        gq = rh.quantize_graph(ns, build(sim=False), 0)
+        shutil.rmtree("output_pt/input")
+        yfq = gq(x).numpy()
+        d["fq_out"] = yfq.astype(np.float32)
+        d["fq_mins"] = np.array([torch.load("output_pt/input/input.%d.min_val.pt" % i) for i in range(6)], dtype=np.float64)
+        d["fq_maxs"] = np.array([torch.load("output_pt/input/input.%d.max_val.pt" % i) for i in range(6)], dtype=np.float64)
+    d["hashes_json"] = np.frombuffer(json.dumps(hashes).encode(), dtype=np.uint8)
+    np.savez_compressed(out, **d)
+    rep = dict(case=name, ok=all(bool(v) for v in checks.values()), checks={k: bool(v) for k, v in checks.items()},
+               activity=act, hashes=hashes, scales=[float(s) for s in scales], zeros=[int(z) for z in zeros],
+               M=Ms, n=Ns)
+    with open(out + ".report.json", "w") as f:
+        json.dump(rep, f)
+    print("%s: oracle==reference: %s  (%d checks)" % (name, rep["ok"], len(checks)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case")
+    ap.add_argument("--out")
+    ap.add_argument("--only", nargs="*")
+    a = ap.parse_args()
+    if a.case:
+        worker(a.case, a.out)
+        return
+    os.makedirs(GOLD, exist_ok=True)
+    pin = {}
+    for name in (a.only or CASES):
+        tmp = tempfile.mkdtemp(prefix="sesrq_gold_")
+        out = os.path.join(GOLD, name + ".npz")
+        try:
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--case", name, "--out", out],
+                           cwd=tmp, check=True)
+            with open(out + ".report.json") as f:
+                pin[name] = json.load(f)
+            os.remove(out + ".report.json")
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    pin_path = os.path.join(GOLD, "ORACLE_PIN.json")
+    if a.only and os.path.exists(pin_path):
+        with open(pin_path) as f:
+            old = json.load(f)
+        old.update(pin)
+        pin = old
+    with open(pin_path, "w") as f:
+        json.dump(pin, f, indent=1, sort_keys=True)
+    bad = [k for k, v in pin.items() if not v["ok"]]
+    print("ORACLE PIN:", "ALL OK" if not bad else "FAILED: %s" % bad)
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
