@@ -1,0 +1,357 @@
+// C ABI of libsesrq: network handle, host-side constant folding, forward orchestration.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+#include "sesrq_internal.h"
+
+namespace sesrq {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local std::string t_cuda_error;
+
+void set_cuda_error(cudaError_t e, const char* where) {
+  t_cuda_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + where;
+}
+const char* get_cuda_error() { return t_cuda_error.c_str(); }
+
+static const int kNextDomain[SESRQ_NUM_LAYERS] = {1, 2, 3, 1, 5};   // quan_func.py:525,601,556,579
+
+// exact range of the per-PE and total partial sums over all codes q in [-128,127]
+static void clamp_bounds(const int8_t* w, int cout, int cin, int k, int acc_bits, int add_bits,
+                         bool* inert_acc, bool* inert_add) {
+  const long long lo_acc = -(1LL << (acc_bits - 1)), hi_acc = (1LL << (acc_bits - 1)) - 1;
+  const long long lo_add = -(1LL << (add_bits - 1)), hi_add = (1LL << (add_bits - 1)) - 1;
+  *inert_acc = true;
+  *inert_add = true;
+  for (int co = 0; co < cout; ++co) {
+    long long hi_p[4] = {0, 0, 0, 0}, lo_p[4] = {0, 0, 0, 0};
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < k * k; ++t) {
+        long long wv = w[((size_t)co * cin + c) * k * k + t];
+        long long a = wv * -128, b = wv * 127;
+        hi_p[c & 3] += std::max(a, b);
+        lo_p[c & 3] += std::min(a, b);
+      }
+    long long hi = 0, lo = 0;
+    for (int p = 0; p < 4; ++p) {
+      if (hi_p[p] > hi_acc || lo_p[p] < lo_acc) *inert_acc = false;
+      hi += hi_p[p];
+      lo += lo_p[p];
+    }
+    if (hi > hi_add || lo < lo_add) *inert_add = false;
+  }
+}
+
+}  // namespace sesrq
+
+using namespace sesrq;
+
+struct SesrqNet {
+  SesrqNetDesc desc;
+  LayerDev layers[SESRQ_NUM_LAYERS];
+  std::vector<int8_t> h_w[SESRQ_NUM_LAYERS];
+  bool need_rc = false;       // z_1 != -128: shortcut codes differ from q_1 (quan_func.py:250 vs :280)
+  bool need_a0 = false;       // layer 0 runs on the generic path -> separate input-quantise pass
+  int device = 0;
+  size_t chunk_bytes = 48u << 20;
+  // host-call staging (sesrq_net_forward_i8_host)
+  void* d_stage = nullptr;
+  size_t stage_bytes = 0;
+};
+
+namespace {
+
+struct WsPlan {
+  int chunk;                 // frames per pass
+  size_t act_bytes;          // one NHWC16 activation buffer for `chunk` frames
+  size_t off_a[5];           // A0..A4
+  size_t off_rc;
+  size_t total;
+};
+
+WsPlan plan_ws(const SesrqNet* net, int B, int H, int W) {
+  WsPlan p{};
+  size_t per_frame = (size_t)H * W * 16;
+  int nbuf = 4 + (net->need_a0 ? 1 : 0) + (net->need_rc ? 1 : 0);
+  size_t per_frame_all = per_frame * nbuf;
+  long long c = per_frame_all ? (long long)(net->chunk_bytes / per_frame_all) : 1;
+  p.chunk = (int)std::max<long long>(1, std::min<long long>(c, std::max(B, 1)));
+  p.act_bytes = (per_frame * p.chunk + 255) & ~(size_t)255;
+  size_t off = 0;
+  for (int i = 0; i < 5; ++i) {
+    p.off_a[i] = off;
+    if (i > 0 || net->need_a0) off += p.act_bytes;
+  }
+  p.off_rc = off;
+  if (net->need_rc) off += p.act_bytes;
+  p.total = off;
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sesrq_abi_version(void) { return SESRQ_ABI_VERSION; }
+
+const char* sesrq_strerror(int code) {
+  switch (code) {
+    case SESRQ_OK: return "ok";
+    case SESRQ_EINVAL: return "invalid argument or unsupported shape";
+    case SESRQ_ENOMEM: return "workspace too small or out of memory";
+    case SESRQ_ECUDA: return "CUDA runtime error";
+    case SESRQ_EARCH: return "device is not an sm_100 (B200) GPU";
+    case SESRQ_EUNSUPPORTED: return "operation not supported in this configuration";
+    default: return "unknown error";
+  }
+}
+
+const char* sesrq_last_cuda_error(void) { return get_cuda_error(); }
+uint64_t sesrq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int sesrq_net_create(const SesrqNetDesc* d, SesrqNet** out_net) {
+  if (!d || !out_net) return SESRQ_EINVAL;
+  *out_net = nullptr;
+  if (d->abi_version != SESRQ_ABI_VERSION || d->n_layers != SESRQ_NUM_LAYERS) return SESRQ_EINVAL;
+  if (d->pe_num != 4 || d->quan_bits != 8) return SESRQ_EINVAL;              // define.py:5 "only 4 PEs"
+  if (d->pe_acc_bits < 9 || d->pe_acc_bits > 30 || d->pe_add_bits < 9 || d->pe_add_bits > 30) return SESRQ_EINVAL;
+  if (d->r_shuffle < 1 || d->r_shuffle > 4) return SESRQ_EINVAL;
+  for (int i = 0; i < SESRQ_NUM_LAYERS; ++i) {
+    const SesrqLayerDesc& l = d->layers[i];
+    if ((l.ksize != 3 && l.ksize != 5) || l.cin < 1 || l.cin > SESRQ_MAX_CH || l.cout < 1 ||
+        l.cout > SESRQ_MAX_CH || !l.h_weight)
+      return SESRQ_EINVAL;
+    if (l.m16 < 0 || l.m16 > 65535 || l.shift_n < -16 || l.shift_n > 32) return SESRQ_EINVAL;
+    if (i > 0 && l.cin != d->layers[i - 1].cout) return SESRQ_EINVAL;
+  }
+  if (d->layers[0].cout != d->layers[3].cout) return SESRQ_EINVAL;           // shortcut add needs equal channels
+  if (d->layers[4].cout % (d->r_shuffle * d->r_shuffle) != 0) return SESRQ_EINVAL;
+
+  int dev = 0;
+  SESRQ_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SESRQ_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return SESRQ_EARCH;
+
+  SesrqNet* net = new (std::nothrow) SesrqNet();
+  if (!net) return SESRQ_ENOMEM;
+  net->desc = *d;
+  net->device = dev;
+  if (const char* e = getenv("SESRQ_CHUNK_MB")) {
+    long v = atol(e);
+    if (v > 0) net->chunk_bytes = (size_t)v << 20;
+  }
+  int zs[SESRQ_NUM_DOMAINS];
+  for (int i = 0; i < SESRQ_NUM_LAYERS; ++i) zs[i] = d->layers[i].z_in;
+  zs[5] = d->z_out;
+  net->need_rc = (zs[1] != -128);
+
+  int rc = SESRQ_OK;
+  for (int i = 0; i < SESRQ_NUM_LAYERS && rc == SESRQ_OK; ++i) {
+    const SesrqLayerDesc& l = d->layers[i];
+    LayerDev& L = net->layers[i];
+    LayerConst& c = L.c;
+    memset(&c, 0, sizeof(c));
+    const int taps = l.ksize * l.ksize;
+    net->h_w[i].assign(l.h_weight, l.h_weight + (size_t)l.cout * l.cin * taps);
+    net->desc.layers[i].h_weight = net->h_w[i].data();
+    const int8_t* w = net->h_w[i].data();
+    c.k = l.ksize;
+    c.pad = (l.ksize - 1) / 2;
+    c.cin = l.cin;
+    c.cout = l.cout;
+    c.pad_byte = std::max(l.z_in, -128) + 128;                                 // quan_func.py:351-352
+    if (c.pad_byte > 255) { rc = SESRQ_EINVAL; break; }
+    c.lo_acc = -(1 << (d->pe_acc_bits - 1));
+    c.hi_acc = (1 << (d->pe_acc_bits - 1)) - 1;
+    c.lo_add = -(1 << (d->pe_add_bits - 1));
+    c.hi_add = (1 << (d->pe_add_bits - 1)) - 1;
+    bool inert_acc, inert_add;
+    clamp_bounds(w, l.cout, l.cin, l.ksize, d->pe_acc_bits, d->pe_add_bits, &inert_acc, &inert_add);
+    c.pe_exact = (inert_acc && inert_add) ? 0 : 1;
+    c.epi = (i == 3) ? EPI_RESIDUAL : (i == 4 ? EPI_FINAL : EPI_PLAIN);
+    c.relu = l.relu;
+    c.save_rc = (i == 0 && net->need_rc) ? 1 : 0;
+    c.r_shuffle = d->r_shuffle;
+    c.mf = (float)((double)l.m16 * std::ldexp(1.0, -l.shift_n));               // exact: m16 < 2^16
+    // layer 3 requantises into domain 1 (:554-560) but its codes are consumed by the residual
+    // quantiser of layer 4, which adds z_4 (:270); z_next is unused by EPI_RESIDUAL.
+    c.z_next = (float)zs[i == 3 ? 4 : kNextDomain[i]];
+    c.res_mf = (float)((double)d->res_m16 * std::ldexp(1.0, -d->res_shift_n));
+    c.z_res = (float)zs[4];
+    c.s_out = (float)d->scale_out;
+    c.in_scale = (float)d->scale_in;
+    c.in_zero = (float)zs[0];
+    for (int co = 0; co < l.cout; ++co) {
+      long long sum_p[4] = {0, 0, 0, 0};
+      for (int ci = 0; ci < l.cin; ++ci)
+        for (int t = 0; t < taps; ++t) sum_p[ci & 3] += w[((size_t)co * l.cin + ci) * taps + t];
+      long long fused = l.add_const[co];
+      for (int p = 0; p < 4; ++p) {
+        c.pe_corr[p][co] = (int32_t)(-128 * sum_p[p]);
+        fused += c.pe_corr[p][co];
+      }
+      c.add_const[co] = l.add_const[co];
+      c.fused_const[co] = (int32_t)fused;
+    }
+    // generic-path weights: [tap][co][pe] words, byte m of word p = W[co][4m + p][tap]
+    std::vector<int32_t> wpk((size_t)taps * 16 * 4, 0);
+    for (int t = 0; t < taps; ++t)
+      for (int co = 0; co < l.cout; ++co)
+        for (int p = 0; p < 4; ++p) {
+          uint32_t word = 0;
+          for (int m = 0; m < 4; ++m) {
+            int ci = 4 * m + p;
+            int8_t v = (ci < l.cin) ? w[((size_t)co * l.cin + ci) * taps + t] : (int8_t)0;
+            word |= (uint32_t)(uint8_t)v << (8 * m);
+          }
+          wpk[((size_t)t * 16 + co) * 4 + p] = (int32_t)word;
+        }
+    if (cudaMalloc(&L.d_wpk, wpk.size() * 4) != cudaSuccess ||
+        cudaMemcpy(L.d_wpk, wpk.data(), wpk.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_cuda_error(cudaGetLastError(), "weight upload");
+      rc = SESRQ_ECUDA;
+      break;
+    }
+    // kernel family
+    L.impl = SESRQ_IMPL_GENERIC;
+    if (d->impl == SESRQ_IMPL_UMMA || d->impl == SESRQ_IMPL_AUTO) {
+      if (umma_supported(c)) {
+        rc = umma_prepare_layer(L, w);
+        if (rc == SESRQ_OK) L.impl = SESRQ_IMPL_UMMA;
+      } else if (d->impl == SESRQ_IMPL_UMMA) {
+        rc = SESRQ_EUNSUPPORTED;
+      }
+    }
+  }
+  if (rc != SESRQ_OK) {
+    sesrq_net_destroy(net);
+    return rc;
+  }
+  net->need_a0 = (net->layers[0].impl == SESRQ_IMPL_GENERIC);
+  *out_net = net;
+  return SESRQ_OK;
+}
+
+void sesrq_net_destroy(SesrqNet* net) {
+  if (!net) return;
+  for (int i = 0; i < SESRQ_NUM_LAYERS; ++i) {
+    if (net->layers[i].d_wpk) cudaFree(net->layers[i].d_wpk);
+    if (net->layers[i].d_wumma) cudaFree(net->layers[i].d_wumma);
+  }
+  if (net->d_stage) cudaFree(net->d_stage);
+  delete net;
+}
+
+int sesrq_net_layer_info(const SesrqNet* net, int layer, int32_t* impl, int32_t* pe_exact) {
+  if (!net || layer < 0 || layer >= SESRQ_NUM_LAYERS) return SESRQ_EINVAL;
+  if (impl) *impl = net->layers[layer].impl;
+  if (pe_exact) *pe_exact = net->layers[layer].c.pe_exact;
+  return SESRQ_OK;
+}
+
+size_t sesrq_ws_bytes(const SesrqNet* net, int B, int H, int W) {
+  if (!net || B < 0 || H <= 0 || W <= 0) return 0;
+  return plan_ws(net, B, H, W).total;
+}
+
+int sesrq_net_forward_i8(const SesrqNet* net, const float* d_x, int B, int H, int W, int8_t* d_q5,
+                         float* d_y, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!net || B < 0 || H <= 0 || W <= 0) return SESRQ_EINVAL;
+  if (B == 0) return SESRQ_OK;
+  if (!d_x || !d_ws) return SESRQ_EINVAL;
+  if ((long long)H * W > (1LL << 30)) return SESRQ_EINVAL;
+  WsPlan p = plan_ws(net, B, H, W);
+  if (ws_bytes < p.total) return SESRQ_ENOMEM;
+  if ((reinterpret_cast<uintptr_t>(d_ws) & 15) != 0) return SESRQ_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_ws);
+  uint8_t* A[5];
+  for (int i = 0; i < 5; ++i) A[i] = ws + p.off_a[i];
+  uint8_t* RC = net->need_rc ? ws + p.off_rc : nullptr;
+  const int cin = net->layers[0].c.cin, cout = net->layers[4].c.cout;
+  const int r = net->desc.r_shuffle;
+  const size_t hw = (size_t)H * W;
+
+  for (int b0 = 0; b0 < B; b0 += p.chunk) {
+    const int nb = std::min(p.chunk, B - b0);
+    const float* x = d_x + (size_t)b0 * cin * hw;
+    int8_t* q5 = d_q5 ? d_q5 + (size_t)b0 * cout * hw : nullptr;
+    float* y = d_y ? d_y + (size_t)b0 * cout * hw : nullptr;     // Cout/r^2 * rH * rW == Cout * H * W
+    (void)r;
+    int rc;
+    // layer 0
+    if (net->layers[0].impl == SESRQ_IMPL_UMMA) {
+      rc = launch_conv_umma(net->layers[0], x, nullptr, nullptr, A[1], nullptr, nullptr, nb, H, W, st);
+    } else {
+      rc = launch_quant_input(x, nb, cin, H, W, net->layers[0].c.in_scale, net->layers[0].c.in_zero, A[0], st);
+      if (rc) return rc;
+      rc = launch_conv_generic(net->layers[0], A[0], nullptr, A[1], RC, nullptr, nullptr, nb, H, W, st);
+    }
+    if (rc) return rc;
+    // layers 1..4
+    for (int i = 1; i < SESRQ_NUM_LAYERS; ++i) {
+      const LayerDev& L = net->layers[i];
+      const uint8_t* sc = (i == 3) ? (net->need_rc ? RC : A[1]) : nullptr;
+      uint8_t* out = (i < 4) ? A[i + 1] : nullptr;
+      if (L.impl == SESRQ_IMPL_UMMA)
+        rc = launch_conv_umma(L, nullptr, A[i], sc, out, i == 4 ? q5 : nullptr, i == 4 ? y : nullptr, nb, H, W, st);
+      else
+        rc = launch_conv_generic(L, A[i], sc, out, nullptr, i == 4 ? q5 : nullptr, i == 4 ? y : nullptr, nb, H, W, st);
+      if (rc) return rc;
+    }
+  }
+  return SESRQ_OK;
+}
+
+int sesrq_ws_read_act_i8(const SesrqNet* net, const void* d_ws, size_t ws_bytes, int B, int H, int W,
+                         int domain, int8_t* d_q_nchw, void* stream) {
+  if (!net || !d_ws || !d_q_nchw || domain < 0 || domain > 4 || B <= 0) return SESRQ_EINVAL;
+  WsPlan p = plan_ws(net, B, H, W);
+  if (ws_bytes < p.total) return SESRQ_ENOMEM;
+  if (B > p.chunk) return SESRQ_EUNSUPPORTED;        // chunked forward reuses the buffers
+  if (domain == 0 && !net->need_a0) return SESRQ_EUNSUPPORTED;   // fused into the layer-0 kernel
+  const int C = (domain == 0) ? net->layers[0].c.cin : net->layers[domain - 1].c.cout;
+  const uint8_t* act = static_cast<const uint8_t*>(d_ws) + p.off_a[domain];
+  return launch_act_to_nchw(act, B, C, H, W, d_q_nchw, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sesrq_net_forward_i8_host(SesrqNet* net, const float* h_x, int B, int H, int W, int8_t* h_q5,
+                              float* h_y, void* stream) {
+  if (!net || B < 0 || H <= 0 || W <= 0) return SESRQ_EINVAL;
+  if (B == 0) return SESRQ_OK;
+  if (!h_x) return SESRQ_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t hw = (size_t)H * W;
+  const int cin = net->layers[0].c.cin, cout = net->layers[4].c.cout;
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t x_bytes = up((size_t)B * cin * hw * 4);
+  const size_t q_bytes = h_q5 ? up((size_t)B * cout * hw) : 0;
+  const size_t y_bytes = h_y ? up((size_t)B * cout * hw * 4) : 0;
+  const size_t ws_bytes = sesrq_ws_bytes(net, B, H, W);
+  const size_t need = x_bytes + q_bytes + y_bytes + ws_bytes;
+  if (need > net->stage_bytes) {
+    if (net->d_stage) SESRQ_CUDA(cudaFree(net->d_stage));
+    net->d_stage = nullptr;
+    net->stage_bytes = 0;
+    SESRQ_CUDA(cudaMalloc(&net->d_stage, need));
+    net->stage_bytes = need;
+  }
+  uint8_t* base = static_cast<uint8_t*>(net->d_stage);
+  float* d_x = reinterpret_cast<float*>(base);
+  int8_t* d_q5 = h_q5 ? reinterpret_cast<int8_t*>(base + x_bytes) : nullptr;
+  float* d_y = h_y ? reinterpret_cast<float*>(base + x_bytes + q_bytes) : nullptr;
+  void* d_ws = base + x_bytes + q_bytes + y_bytes;
+  SESRQ_CUDA(cudaMemcpyAsync(d_x, h_x, (size_t)B * cin * hw * 4, cudaMemcpyHostToDevice, st));
+  int rc = sesrq_net_forward_i8(net, d_x, B, H, W, d_q5, d_y, d_ws, ws_bytes, stream);
+  if (rc) return rc;
+  if (h_q5) SESRQ_CUDA(cudaMemcpyAsync(h_q5, d_q5, (size_t)B * cout * hw, cudaMemcpyDeviceToHost, st));
+  if (h_y) SESRQ_CUDA(cudaMemcpyAsync(h_y, d_y, (size_t)B * cout * hw * 4, cudaMemcpyDeviceToHost, st));
+  SESRQ_CUDA(cudaStreamSynchronize(st));
+  return SESRQ_OK;
+}
+
+}  // extern "C"
