@@ -1,8 +1,469 @@
-// tcgen05 implicit-GEMM conv path (placeholder until the kernel lands in this round).
+// tcgen05 implicit-GEMM convolution for the 16-channel layers (sm_100a only).
+//
+// Data flow per CTA (persistent, one CTA per SM, warp-specialised):
+//   warp 0      TMA producer: one cp.async.bulk.tensor.4d per tile brings the (TH+2p) x (TW+2p) x 16 B halo
+//               tile of NHWC16 bytes into shared memory; out-of-frame pixels are zero-filled by TMA, and
+//               byte 0 == code -128 == the reference's pad value z' (quan_func.py:351-352), so padding is free.
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::i8 (u8 activations x s8 weights -> s32 in
+//               TMEM).  No im2col: the tile is pixel-major (16 B per pixel), so the A operand of tap (dy,dx)
+//               for 128 consecutive output positions is the same tile shifted by (dy*pitch+dx) pixels.  A K=32
+//               instruction covers two taps: its canonical no-swizzle K-major descriptor takes the two 16-byte
+//               K chunks LBO bytes apart, and LBO is simply the distance between the two taps.  Output positions
+//               are linearised over the padded pitch, so every 128-row operand is one uniform-stride run
+//               (SBO = 128 B); the 2p garbage columns per row are discarded by the epilogue.
+//   warp 2      TMEM allocator (512 columns = 32 accumulator slots of 128 x 16, or 8 of 128 x 64).
+//   warps 4..   epilogue: tcgen05.ld (lane = pixel, column = output channel), exact requant arithmetic of
+//               SURVEY App. A, 16-byte NHWC16 store (or int8 NCHW + pixel-shuffled fp32 for the last layer).
+// PE semantics: with pe_exact the B operand carries four copies of the weights, each masked to the input
+// channels of one PE (N = 64), so the four per-PE partial sums land in separate TMEM columns and are clamped
+// to PE_ACC_BIT individually before the adder tree -- same instruction count, the tensor pipe has the headroom.
+#include <cuda.h>
+#include <algorithm>
+#include <cstring>
+#include <vector>
 #include "sesrq_internal.h"
+
 namespace sesrq {
-bool umma_supported(const LayerConst&) { return false; }
-int umma_prepare_layer(LayerDev&, const int8_t*) { return SESRQ_EUNSUPPORTED; }
-int launch_conv_umma(const LayerDev&, const float*, const uint8_t*, const uint8_t*, uint8_t*, int8_t*, float*,
-                     int, int, int, cudaStream_t) { return SESRQ_EUNSUPPORTED; }
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t a = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(a), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------------
+constexpr int UMMA_M = 128;
+constexpr int MAX_PAIRS = 13;            // ceil(25 / 2)
+constexpr int TMEM_COLS = 512;
+constexpr int CTRL_WARPS = 4;            // producer, MMA, allocator, spare (keeps epilogue warp % 4 == lane quarter)
+
+struct UmmaParams {
+  // per-column epilogue constants (column n of the accumulator <-> output channel col_chan[n])
+  int32_t col_const[16];                 // fused_const (fast) or add_const (pe_exact) of that channel
+  int32_t col_pe_corr[4][16];
+  int32_t lo_acc, hi_acc, lo_add, hi_add;
+  float mf, z_next, res_mf, z_res, s_out;
+  int32_t relu, cout, r_shuffle;
+  // geometry
+  int32_t B, H, W, TH, TW, pitch, tiles_x, tiles_y, num_tiles, nblk, pad;
+  uint32_t box_bytes, stage_bytes, w_bytes;
+  int32_t n_pairs;
+  int32_t pair_off[MAX_PAIRS];           // pixel offset of the first tap of the pair inside the tile
+  int32_t pair_lbo[MAX_PAIRS];           // pixel distance to the second tap
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout NONE
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int NPE, int EPI, int EPI_WARPS>
+__global__ void __launch_bounds__((CTRL_WARPS + EPI_WARPS) * 32, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ UmmaParams P,
+                 const uint8_t* __restrict__ w_img, const uint4* __restrict__ shortcut, uint4* __restrict__ out,
+                 int8_t* __restrict__ q5, float* __restrict__ y) {
+  constexpr int NCOLS = 16 * NPE;
+  constexpr int NSLOT = TMEM_COLS / NCOLS;
+  constexpr int NWG = EPI_WARPS / 4;
+  static_assert(NSLOT % NWG == 0, "slot ownership must be stable per warpgroup");
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* tile[2] = {smem, smem + P.stage_bytes};
+  uint8_t* w_s = smem + 2 * (size_t)P.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + ((P.w_bytes + 127) & ~127u));
+  uint64_t* tile_full = bars;              // [2]
+  uint64_t* tile_empty = bars + 2;         // [2]
+  uint64_t* acc_full = bars + 4;           // [NSLOT]
+  uint64_t* acc_empty = bars + 4 + NSLOT;  // [NSLOT]
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 4 + 2 * NSLOT);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- one-time setup ----
+  for (uint32_t i = threadIdx.x; i < P.w_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(w_img) + i);
+  fence_proxy_async();                      // weights were written through the generic proxy, UMMA reads via async proxy
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+    mbar_init(&tile_full[0], 1);
+    mbar_init(&tile_full[1], 1);
+    mbar_init(&tile_empty[0], 1);
+    mbar_init(&tile_empty[1], 1);
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);          // one elected arrival per epilogue warp of the owning warpgroup
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_s, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+
+  const int tiles_per_frame = P.tiles_x * P.tiles_y;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
+        const int st = it & 1;
+        mbar_wait(&tile_empty[st], ((it >> 1) & 1) ^ 1);
+        const int b = t / tiles_per_frame;
+        const int r = t - b * tiles_per_frame;
+        const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
+        mbar_arrive_expect_tx(&tile_full[st], P.box_bytes);
+        tma_load_4d(tile[st], &tmap, 0, tx * P.TW - P.pad, ty * P.TH - P.pad, b, &tile_full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t w_addr = smem_u32(w_s);
+      int it = 0;
+      uint32_t g = 0;                       // running accumulator-block counter of this CTA
+      for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
+        const int st = it & 1;
+        mbar_wait(&tile_full[st], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(tile[st]);
+        for (int mb = 0; mb < P.nblk; ++mb, ++g) {
+          const uint32_t slot = g % NSLOT;
+          mbar_wait(&acc_empty[slot], ((g / NSLOT) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + slot * NCOLS;
+          for (int pr = 0; pr < P.n_pairs; ++pr) {
+            const uint64_t ad = make_desc(a_base + (uint32_t)(mb * UMMA_M + P.pair_off[pr]) * 16u,
+                                          (uint32_t)P.pair_lbo[pr] * 16u, 128u);
+            const uint64_t bd = make_desc(w_addr + (uint32_t)pr * (2u * NCOLS * 16u), NCOLS * 16u, 128u);
+            umma_i8(d, ad, bd, P.idesc, pr > 0 ? 1u : 0u);
+          }
+          umma_commit(&acc_full[slot]);     // implies tcgen05.fence::before_thread_sync
+        }
+        umma_commit(&tile_empty[st]);       // the tile buffer is free once every MMA that reads it has retired
+      }
+    }
+  } else if (warp >= CTRL_WARPS) {
+    // ================= epilogue =================
+    const int ew = warp - CTRL_WARPS;
+    const int wg = ew >> 2;                 // warpgroup
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const long long HW = (long long)P.H * P.W;
+    uint32_t g0 = 0;                        // accumulator-block counter at the start of the current tile
+    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+      const int b = t / tiles_per_frame;
+      const int r = t - b * tiles_per_frame;
+      const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
+      const int y0 = ty * P.TH, x0 = tx * P.TW;
+      for (int mb = 0; mb < P.nblk; ++mb) {
+        const uint32_t g = g0 + mb;
+        if ((int)(g % NWG) != wg) continue;
+        const uint32_t slot = g % NSLOT;
+        const int L = mb * UMMA_M + quarter * 32 + lane;
+        const int oy = L / P.pitch, ox = L - oy * P.pitch;
+        const int gy = y0 + oy, gx = x0 + ox;
+        const bool valid = (ox < P.TW) && (oy < P.TH) && (gy < P.H) && (gx < P.W);
+        const long long pix = (long long)b * HW + (long long)gy * P.W + gx;
+        uint4 sc = make_uint4(0u, 0u, 0u, 0u);
+        if (EPI == EPI_RESIDUAL && valid) sc = __ldg(shortcut + pix);
+
+        mbar_wait(&acc_full[slot], (g / NSLOT) & 1);
+        tc_fence_after();
+        int acc[NPE][16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * NCOLS;
+#pragma unroll
+        for (int p = 0; p < NPE; ++p) tmem_ld16(taddr + p * 16, acc[p]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[slot]);
+
+        if (!valid) continue;
+        const uint32_t scw[4] = {sc.x, sc.y, sc.z, sc.w};
+        uint32_t ow[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+          int A;
+          if (NPE == 1) {
+            A = acc[0][n] + P.col_const[n];
+          } else {
+            int s = 0;
+#pragma unroll
+            for (int p = 0; p < NPE; ++p) s += clampi(acc[p][n] + P.col_pe_corr[p][n], P.lo_acc, P.hi_acc);
+            A = clampi(s, P.lo_add, P.hi_add) + P.col_const[n];
+          }
+          const float yv = requant(A, P.mf);
+          if (EPI == EPI_FINAL) {
+            if (n < P.cout) {               // columns are in natural channel order for the last layer
+              const int q = quant_add_zero(yv, P.z_next);
+              if (q5) q5[((long long)b * P.cout + n) * HW + (long long)gy * P.W + gx] = (int8_t)q;
+              if (y) {
+                const float o = __fmul_rn(__fsub_rn((float)q, P.z_next), P.s_out);
+                const int rr = P.r_shuffle, r2 = rr * rr;
+                const int cc = n / r2, ii = (n % r2) / rr, jj = n % rr;
+                const int Co = P.cout / r2;
+                y[(((long long)b * Co + cc) * (P.H * rr) + (gy * rr + ii)) * (long long)(P.W * rr) + (gx * rr + jj)] = o;
+              }
+            }
+          } else {
+            const float a = P.relu ? fmaxf(yv, 0.f) : yv;
+            int v;
+            if (EPI == EPI_RESIDUAL) {
+              const int ic = quant_add_zero(a, -128.f);
+              const int vrc = (scw[n >> 2] >> (8 * (n & 3))) & 0xff;
+              const float tt = __fmul_rn((float)(vrc + ic + 128), P.res_mf);
+              v = quant_add_zero(tt, P.z_res) + 128;
+            } else {
+              v = quant_add_zero(a, P.z_next) + 128;
+            }
+            ow[n >> 2] |= (uint32_t)v << (8 * (n & 3));
+          }
+        }
+        if (EPI != EPI_FINAL) out[pix] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+      g0 += P.nblk;
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool umma_supported(const LayerConst& c) {
+  // 16 input channels from an NHWC16 tensor whose out-of-frame value is byte 0 (z' == -128);
+  // layer 0 (fp32 input, cin < 16) and other zero points run on the generic path.
+  return c.cin == 16 && c.pad_byte == 0 && c.save_rc == 0 && (c.k == 3 || c.k == 5);
+}
+
+// B operand image: for every tap pair, [2 K-halves][N/8 row groups][8 rows][16 B]; row n of PE copy p holds
+// the weights of output channel col_chan(n) for the 16 input-channel bytes (masked to word p when pe_exact).
+int umma_prepare_layer(LayerDev& L, const int8_t* w) {
+  const LayerConst& c = L.c;
+  const int taps = c.k * c.k, pairs = (taps + 1) / 2;
+  const int npe = c.pe_exact ? 4 : 1;
+  const int N = 16 * npe;
+  L.umma_n = N;
+  std::vector<uint8_t> img((size_t)pairs * 2 * N * 16, 0);
+  const bool natural = (c.epi == EPI_FINAL);
+  for (int pr = 0; pr < pairs; ++pr)
+    for (int h = 0; h < 2; ++h) {
+      const int t = 2 * pr + h;
+      if (t >= taps) continue;
+      for (int n = 0; n < N; ++n) {
+        const int p = n / 16, nn = n % 16;
+        const int co = natural ? nn : chan_of_byte(nn);
+        if (co >= c.cout) continue;
+        uint8_t* row = img.data() + (((size_t)pr * 2 + h) * N + n) * 16;
+        for (int j = 0; j < 16; ++j) {
+          const int ci = chan_of_byte(j);
+          if (ci >= c.cin) continue;
+          if (npe == 4 && (j >> 2) != p) continue;
+          row[j] = (uint8_t)w[((size_t)co * c.cin + ci) * taps + t];
+        }
+      }
+    }
+  if (cudaMalloc(&L.d_wumma, img.size()) != cudaSuccess ||
+      cudaMemcpy(L.d_wumma, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_cuda_error(cudaGetLastError(), "umma weight upload");
+    return SESRQ_ECUDA;
+  }
+  return SESRQ_OK;
+}
+
+template <int NPE, int EPI, int EPI_WARPS>
+static int launch_one(const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L, const uint8_t* d_shortcut,
+                      uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem, cudaStream_t st) {
+  auto kern = conv_umma_kernel<NPE, EPI, EPI_WARPS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SESRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  kern<<<grid, (CTRL_WARPS + EPI_WARPS) * 32, smem, st>>>(tmap, P, L.d_wumma, reinterpret_cast<const uint4*>(d_shortcut),
+                                                          reinterpret_cast<uint4*>(d_out), d_q5, d_y);
+  SESRQ_LAUNCH_CHECK("conv_umma_kernel");
+  return SESRQ_OK;
+}
+
+int launch_conv_umma(const LayerDev& L, const float* /*d_x*/, const uint8_t* d_in, const uint8_t* d_shortcut,
+                     uint8_t* d_out, int8_t* d_q5, float* d_y, int B, int H, int W, cudaStream_t st) {
+  const LayerConst& c = L.c;
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return SESRQ_EUNSUPPORTED;
+  if (!d_in) return SESRQ_EINVAL;
+  const int pad = c.pad;
+  const int npe = c.pe_exact ? 4 : 1;
+  const int N = 16 * npe;
+
+  // ---- tiling ----
+  UmmaParams P;
+  memset(&P, 0, sizeof(P));
+  const int max_tw = 256 - 2 * pad;
+  P.tiles_x = cdiv(W, std::min(W, 240 > max_tw ? max_tw : 240));
+  P.TW = cdiv(W, P.tiles_x);
+  P.pitch = P.TW + 2 * pad;
+  const int taps = c.k * c.k, pairs = (taps + 1) / 2;
+  const uint32_t w_bytes = (uint32_t)pairs * 2 * N * 16;
+  const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (4 + 2 * (TMEM_COLS / N)) + 64 + 1024;
+  const size_t budget = (227 * 1024 - fixed) / 2;                    // per tile stage
+  // rows per tile: as many as fit (<= 32), balanced over the frame
+  int th_max = (int)((budget / 16 - 2 * pad - 128) / P.pitch) - 2 * pad;
+  th_max = std::max(1, std::min(th_max, 32));
+  P.tiles_y = cdiv(H, std::min(H, th_max));
+  P.TH = cdiv(H, P.tiles_y);
+  P.nblk = cdiv((P.TH - 1) * P.pitch + P.TW, UMMA_M);
+  P.stage_bytes = (uint32_t)((((size_t)P.nblk * UMMA_M + 2 * pad * P.pitch + 2 * pad) * 16 + 1023) & ~(size_t)1023);
+  P.box_bytes = (uint32_t)((P.TH + 2 * pad) * P.pitch * 16);
+  if ((size_t)P.stage_bytes * 2 + fixed > 227 * 1024 || P.TH + 2 * pad > 256) return SESRQ_EUNSUPPORTED;
+  P.w_bytes = w_bytes;
+  P.num_tiles = P.tiles_x * P.tiles_y * B;
+  P.B = B; P.H = H; P.W = W; P.pad = pad;
+  P.n_pairs = pairs;
+  for (int pr = 0; pr < pairs; ++pr) {
+    const int t0 = 2 * pr, t1 = 2 * pr + 1;
+    const int o0 = (t0 / c.k) * P.pitch + (t0 % c.k);
+    const int o1 = (t1 < taps) ? (t1 / c.k) * P.pitch + (t1 % c.k) : o0 + 1;   // dummy half: weights are zero
+    P.pair_off[pr] = o0;
+    P.pair_lbo[pr] = o1 - o0;
+  }
+  // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32, A = u8, B = s8, K-major both, N, M = 128
+  P.idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
+  const bool natural = (c.epi == EPI_FINAL);
+  for (int n = 0; n < 16; ++n) {
+    const int co = natural ? n : chan_of_byte(n);
+    if (co < c.cout) {
+      P.col_const[n] = c.pe_exact ? c.add_const[co] : c.fused_const[co];
+      for (int p = 0; p < 4; ++p) P.col_pe_corr[p][n] = c.pe_corr[p][co];
+    }
+  }
+  P.lo_acc = c.lo_acc; P.hi_acc = c.hi_acc; P.lo_add = c.lo_add; P.hi_add = c.hi_add;
+  P.mf = c.mf; P.z_next = c.z_next; P.res_mf = c.res_mf; P.z_res = c.z_res; P.s_out = c.s_out;
+  P.relu = c.relu; P.cout = c.cout; P.r_shuffle = c.r_shuffle;
+
+  // ---- tensor map over the NHWC16 input: dims (16 B, W, H, B) ----
+  CUtensorMap tmap;
+  cuuint64_t gdim[4] = {16, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  cuuint32_t box[4] = {16, (cuuint32_t)P.pitch, (cuuint32_t)(P.TH + 2 * pad), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(d_in), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
+    return SESRQ_ECUDA;
+  }
+
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = std::min(P.num_tiles, sms);
+  const size_t smem = (size_t)P.stage_bytes * 2 + fixed;
+
+#define SESRQ_UMMA_CASE(NPE_, EPI_, EW_) \
+  return launch_one<NPE_, EPI_, EW_>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st)
+  if (npe == 1) {
+    if (c.epi == EPI_PLAIN) SESRQ_UMMA_CASE(1, EPI_PLAIN, 16);
+    if (c.epi == EPI_RESIDUAL) SESRQ_UMMA_CASE(1, EPI_RESIDUAL, 16);
+    SESRQ_UMMA_CASE(1, EPI_FINAL, 16);
+  } else {
+    if (c.epi == EPI_PLAIN) SESRQ_UMMA_CASE(4, EPI_PLAIN, 8);
+    if (c.epi == EPI_RESIDUAL) SESRQ_UMMA_CASE(4, EPI_RESIDUAL, 8);
+    SESRQ_UMMA_CASE(4, EPI_FINAL, 8);
+  }
+#undef SESRQ_UMMA_CASE
+}
+
+}  // namespace sesrq
