@@ -235,6 +235,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         uint4 sc = make_uint4(0u, 0u, 0u, 0u);
         if (EPI == EPI_RESIDUAL && valid) sc = __ldg(shortcut + pix);
 
+        __syncwarp();                        // the .sync.aligned TMEM loads below need a converged warp
         mbar_wait(&acc_full[slot], (g / NSLOT) & 1);
         tc_fence_after();
         int acc[NPE][16];
@@ -246,7 +247,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[slot]);
 
-        if (!valid) continue;
+        if (valid) {
         const uint32_t scw[4] = {sc.x, sc.y, sc.z, sc.w};
         uint32_t ow[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -288,6 +289,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
           }
         }
         if (EPI != EPI_FINAL) out[pix] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }  // valid
       }
       g0 += P.nblk;
     }
