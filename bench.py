@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- SESR int8 hardware-sim throughput on B200 (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--batch B]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (5 fused conv layers: quantise -> int8 conv -> PE tree -> requant ->
+ReLU/residual -> pixel shuffle) over one batch of synthetic frames per GPU.  Default workload = BASELINE.json's
+headline metric: SESR x2 int8 sim on 1080p input (1920x1080 -> 3840x2160).  Frames are sharded data-parallel,
+per-GPU batch fixed (weak scaling), no data-path collective.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (golden case holding weights + thresholds, H, W, default per-GPU batch)
+    "sesr_x2_int8_sim_1080p": ("x2_fixture", 1080, 1920, 16),
+    "sesr_x4_int8_sim_540x960": ("x4_fixture", 540, 960, 64),
+    "nrdm3_int8_sim_80x960": ("nrdm_fixture", 80, 960, 512),
+    "sesr_x2_int8_sim_80x960": ("x2_fixture", 80, 960, 256),
+    "sesr_x4_int8_sim_80x960": ("x4_fixture", 80, 960, 256),
+}
+METRIC = "output Mpixels/sec (SESR x2 int8 sim)"
+
+
+def layer_bytes_per_px(cin, cout, want_q5=True, want_y=True):
+    """Algorithmic HBM bytes per LR pixel, per layer (SURVEY 8d per-layer-fused model): every activation
+    tensor crosses HBM once per direction as int8 NHWC16, fp32 input read once, shortcut re-read once."""
+    last = 16 + (cout if want_q5 else 0) + (4 * cout if want_y else 0)
+    return [4 * cin + 16, 32, 32, 48, last]
+
+
+def load_case(name):
+    from conftest import load_golden
+    return load_golden(name)
+
+
+def sample_clocks_start(gpu_index):
+    f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+        proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                 "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+    except OSError:
+        return None, f.name
+    return proc, f.name
+
+
+def sample_clocks_stop(proc, path):
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    if proc is not None:
+        proc.terminate()
+        try:
+            proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+    try:
+        rows = [r.strip().split(",") for r in open(path) if r.strip()]
+        os.unlink(path)
+    except OSError:
+        rows = []
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for r in rows:
+        try:
+            sm.append(float(r[1]))
+            mx.append(float(r[2]))
+            for k, nm in enumerate(names):
+                if r[5 + k].strip().lower().startswith("active"):
+                    reasons.add(nm)
+        except (ValueError, IndexError):
+            continue
+    if sm:
+        out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm), reasons=sorted(reasons))
+    return out
+
+
+def cpu_reference_time(case, H, W, frames, reps):
+    """Times the CPU restatement of the reference path (oracle/sesr_oracle.c, all host threads) on `frames`
+    frames of the workload shape.  Returns (best seconds, threads)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import c_oracle
+    import sesr_oracle as orc
+    g = load_case(case)
+    onet = orc.derive_net(g.wf, g.bf, g.scales, g.zeros, g.r)
+    cn = c_oracle.CNet(onet)
+    x = np.random.default_rng(4321).random((frames, g.wf[0].shape[1], H, W), dtype=np.float32)
+    best = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        cn.forward(x)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return best, c_oracle.threads()
+
+
+def run_reference(args, case, H, W, r):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    out_px = H * W * r * r
+    frames = 1
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_time(case, H, W, frames, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_time(case, H, W, frames, 1)
+    dt = (time.perf_counter() - t0) / args.steps
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle
+    val = frames * out_px / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "H": H, "W": W, "frames_per_step": frames},
+        "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": c_oracle.threads(), "kind": "port",
+                         "sample": "%d frame(s) of %dx%d per step, C restatement of the reference path "
+                                   "(oracle/sesr_oracle.c, OpenMP); the Python reference cannot travel" % (frames, H, W)},
+        "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sesr_x2_int8_sim_1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (0 = workload default)")
+    ap.add_argument("--kernel-impl", default="auto", choices=["auto", "generic"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    case, H, W, defB = WORKLOADS[args.workload]
+    B = args.batch or defB
+    g = load_case(case)
+    r = g.r
+    cin, cout = g.wf[0].shape[1], g.wf[4].shape[0]
+    out_px_frame = H * W * r * r
+
+    if args.impl == "reference":
+        run_reference(args, case, H, W, r)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from sesr_pytorch_quantize_b200 import Int8Net, compile_network, IMPL_AUTO, IMPL_GENERIC, load_library
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sesrq hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = load_library()
+
+    cnet = compile_network([torch.from_numpy(w) for w in g.wf], [torch.from_numpy(b) for b in g.bf], g.scales, g.zeros, r)
+    net = Int8Net(cnet, device=dev, impl=IMPL_GENERIC if args.kernel_impl == "generic" else IMPL_AUTO)
+    impls = [net.layer_info(i) for i in range(5)]
+
+    gen = torch.Generator().manual_seed(4321 + rank)
+    x_host = torch.rand(B, cin, H, W, generator=gen).pin_memory()
+    x = x_host.to(dev, non_blocking=True)
+    qs, ys = net.out_shapes(B, H, W)
+    q5 = torch.empty(qs, dtype=torch.int8, device=dev)
+    y = torch.empty(ys, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        net(x, q5=q5, y=y)
+    barrier()
+
+    # ---- timed region: K steps, inputs resident in HBM, per-kernel events on the launching stream ----
+    net.profile(True)
+    net.profile_read()
+    proc, cpath = sample_clocks_start(local)
+    time.sleep(0.25)
+    launches0 = lib.sesrq_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        net(x, q5=q5, y=y)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.sesrq_launch_count() - launches0
+    clocks = sample_clocks_stop(proc, cpath)
+    layer_ms, layer_launches = net.profile_read()
+    net.profile(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * B * out_px_frame / (ms_step * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (largest share of the step), live numbers ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    lbytes = layer_bytes_per_px(cin, cout)
+    lr_px_launch = [(B * H * W * args.steps) / max(layer_launches[i], 1) for i in range(5)]
+    per_layer = []
+    for i in range(5):
+        avg_ms = layer_ms[i] / max(layer_launches[i], 1)
+        gbs = lbytes[i] * lr_px_launch[i] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        per_layer.append({"layer": i, "impl": "umma" if impls[i][0] == 2 else "generic", "pe_exact": impls[i][1],
+                          "avg_ms": avg_ms, "launches": layer_launches[i], "alg_bytes_per_lr_px": lbytes[i],
+                          "achieved_gbs": gbs, "share": layer_ms[i] / max(sum(layer_ms), 1e-9)})
+    dom = max(range(5), key=lambda i: layer_ms[i])
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("layer%d" % dom)
+    except (OSError, ValueError):
+        pass
+    roofline = {"bound": "hbm", "kernel": "layer %d (%s)" % (dom, per_layer[dom]["impl"]),
+                "achieved": per_layer[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": per_layer[dom]["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src}
+    stack_gbs = sum(lbytes) * B * H * W / (ms_step * 1e-3) / 1e9
+    total_macs = sum(L.ksize * L.ksize * L.cin * L.cout for L in cnet.layers)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside) ----
+    e2e = None
+    if not args.no_e2e:
+        q5_h = torch.empty(qs, dtype=torch.int8).pin_memory()
+        y_h = torch.empty(ys, dtype=torch.float32).pin_memory()
+        net.forward_host(x_host, q5_h, y_h)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.e2e_steps):
+            net.forward_host(x_host, q5_h, y_h)
+        s1.record()
+        barrier()
+        te = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_ms = float(te.item()) / args.e2e_steps
+        e2e = {"value": world * B * out_px_frame / (e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
+               "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": q5_h.numel() + y_h.numel() * 4,
+               "ms_per_step": e_ms, "api": "sesrq_net_forward_i8_host (Int8Net.forward_host), pinned host buffers"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        secs, thr = cpu_reference_time(case, H, W, 1, 2)
+        cpu = {"value": out_px_frame / secs / 1e6, "unit": "Mpix/s", "cores": thr, "kind": "port",
+               "sample": "1 frame of %dx%d (best of 2), C restatement of the reference path with OpenMP" % (H, W),
+               "s_per_frame": secs}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "frames_per_gpu_per_step": B, "H": H, "W": W, "upscale": r,
+                       "cin": cin, "cout": cout, "outputs": "q5 int8 NCHW + fp32 pixel-shuffled y",
+                       "weights": "reference checkpoint collapsed (tests/golden/%s.npz), reference min/max thresholds" % case,
+                       "input": "torch.rand seed 4321+rank, %.0f MB per step > 126 MB L2 (no L2 flush needed)" % (x.numel() * 4 / 1e6),
+                       "parallelism": "dp%d frames sharded, no collective" % world},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu,
+            "stack": {"alg_bytes_per_lr_px": sum(lbytes), "achieved_gbs": stack_gbs, "frac_of_hbm_peak": stack_gbs / peak,
+                      "int8_tops": 2 * total_macs * B * H * W / (ms_step * 1e-3) / 1e12, "us_per_frame": ms_step * 1e3 / B},
+            "layers": per_layer,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

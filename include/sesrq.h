@@ -114,6 +114,13 @@ int sesrq_net_forward_i8(const SesrqNet* net, const float* d_x, int B, int H, in
 int sesrq_net_forward_i8_host(SesrqNet* net, const float* h_x, int B, int H, int W,
                               int8_t* h_q5, float* h_y, void* stream);
 
+/* Per-kernel device timing: when enabled, every kernel sesrq_net_forward_i8 launches is bracketed by
+ * CUDA events on the launching stream.  sesrq_net_profile_read synchronises on them, adds the elapsed
+ * milliseconds and launch counts per layer into ms[] / launches[] (index SESRQ_NUM_LAYERS = the separate
+ * input-quantise pass of the generic path) and clears the record.  Not thread-safe on one handle. */
+int sesrq_net_profile_enable(SesrqNet* net, int enable);
+int sesrq_net_profile_read(SesrqNet* net, double* ms, uint64_t* launches);
+
 /* Intermediate activations of the LAST sesrq_net_forward_i8 on this workspace, for layer-by-layer
  * parity: writes q_i (the reference's input.{i}.pt, i = 0..4) as int8 NCHW [B,C_i,H,W]. */
 int sesrq_ws_read_act_i8(const SesrqNet* net, const void* d_ws, size_t ws_bytes, int B, int H, int W,

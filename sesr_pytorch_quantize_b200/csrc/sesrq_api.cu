@@ -4,6 +4,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 #include "sesrq_internal.h"
 
@@ -60,7 +61,30 @@ struct SesrqNet {
   // host-call staging (sesrq_net_forward_i8_host)
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
+  // per-kernel event timing (sesrq_net_profile_*)
+  mutable bool profiling = false;
+  struct EvRec { cudaEvent_t a, b; int slot; };
+  mutable std::vector<EvRec> ev_used;
+  mutable std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_free;
 };
+
+namespace {
+// brackets one launch with events when profiling is on
+struct ProfScope {
+  const SesrqNet* net; cudaStream_t st; int slot; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(const SesrqNet* n, cudaStream_t s, int sl) : net(n), st(s), slot(sl) {
+    if (!net->profiling) return;
+    if (!net->ev_free.empty()) { a = net->ev_free.back().first; b = net->ev_free.back().second; net->ev_free.pop_back(); }
+    else if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, st);
+    net->ev_used.push_back({a, b, slot});
+  }
+};
+}  // namespace
 
 namespace {
 
@@ -243,6 +267,8 @@ void sesrq_net_destroy(SesrqNet* net) {
     if (net->layers[i].d_wumma) cudaFree(net->layers[i].d_wumma);
   }
   if (net->d_stage) cudaFree(net->d_stage);
+  for (auto& r : net->ev_used) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& r : net->ev_free) { cudaEventDestroy(r.first); cudaEventDestroy(r.second); }
   delete net;
 }
 
@@ -285,10 +311,15 @@ int sesrq_net_forward_i8(const SesrqNet* net, const float* d_x, int B, int H, in
     int rc;
     // layer 0
     if (net->layers[0].impl == SESRQ_IMPL_UMMA) {
+      ProfScope ps(net, st, 0);
       rc = launch_conv_umma(net->layers[0], x, nullptr, nullptr, A[1], nullptr, nullptr, nb, H, W, st);
     } else {
-      rc = launch_quant_input(x, nb, cin, H, W, net->layers[0].c.in_scale, net->layers[0].c.in_zero, A[0], st);
+      {
+        ProfScope ps(net, st, SESRQ_NUM_LAYERS);
+        rc = launch_quant_input(x, nb, cin, H, W, net->layers[0].c.in_scale, net->layers[0].c.in_zero, A[0], st);
+      }
       if (rc) return rc;
+      ProfScope ps(net, st, 0);
       rc = launch_conv_generic(net->layers[0], A[0], nullptr, A[1], RC, nullptr, nullptr, nb, H, W, st);
     }
     if (rc) return rc;
@@ -297,6 +328,7 @@ int sesrq_net_forward_i8(const SesrqNet* net, const float* d_x, int B, int H, in
       const LayerDev& L = net->layers[i];
       const uint8_t* sc = (i == 3) ? (net->need_rc ? RC : A[1]) : nullptr;
       uint8_t* out = (i < 4) ? A[i + 1] : nullptr;
+      ProfScope ps(net, st, i);
       if (L.impl == SESRQ_IMPL_UMMA)
         rc = launch_conv_umma(L, nullptr, A[i], sc, out, i == 4 ? q5 : nullptr, i == 4 ? y : nullptr, nb, H, W, st);
       else
@@ -304,6 +336,26 @@ int sesrq_net_forward_i8(const SesrqNet* net, const float* d_x, int B, int H, in
       if (rc) return rc;
     }
   }
+  return SESRQ_OK;
+}
+
+int sesrq_net_profile_enable(SesrqNet* net, int enable) {
+  if (!net) return SESRQ_EINVAL;
+  net->profiling = enable != 0;
+  return SESRQ_OK;
+}
+
+int sesrq_net_profile_read(SesrqNet* net, double* ms, uint64_t* launches) {
+  if (!net || !ms || !launches) return SESRQ_EINVAL;
+  for (auto& r : net->ev_used) {
+    SESRQ_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    SESRQ_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.slot] += t;
+    launches[r.slot] += 1;
+    net->ev_free.emplace_back(r.a, r.b);
+  }
+  net->ev_used.clear();
   return SESRQ_OK;
 }
 

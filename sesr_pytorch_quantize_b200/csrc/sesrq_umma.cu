@@ -1,17 +1,21 @@
 // tcgen05 implicit-GEMM convolution for the 16-channel layers (sm_100a only).
 //
 // Data flow per CTA (persistent, one CTA per SM, warp-specialised):
-//   warp 0      TMA producer: one cp.async.bulk.tensor.4d per tile brings the (TH+2p) x (TW+2p) x 16 B halo
-//               tile of NHWC16 bytes into shared memory; out-of-frame pixels are zero-filled by TMA, and
-//               byte 0 == code -128 == the reference's pad value z' (quan_func.py:351-352), so padding is free.
-//   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::i8 (u8 activations x s8 weights -> s32 in
+//   warp 0      TMA producer: one cp.async.bulk.tensor.3d per tile brings a (TH+2p)-row x 128-pixel halo tile of
+//               NHWC16 bytes into shared memory.  The tensor map views a frame row as W*2 8-byte elements so
+//               the box's inner extent is a contiguous 2048-byte run (a 16-byte inner box makes TMA fetch one
+//               32-byte sector per pixel: measured 2x traffic and ~10x slower, profiles/r1a).  Out-of-frame
+//               pixels are zero-filled by TMA, and byte 0 == code -128 == the reference's pad value z'
+//               (quan_func.py:351-352), so padding is free.
+//   warps 1-3   MMA issuers (accumulator blocks dealt round-robin): one elected thread per warp issues tcgen05.mma.kind::i8 (u8 activations x s8 weights -> s32 in
 //               TMEM).  No im2col: the tile is pixel-major (16 B per pixel), so the A operand of tap (dy,dx)
 //               for 128 consecutive output positions is the same tile shifted by (dy*pitch+dx) pixels.  A K=32
 //               instruction covers two taps: its canonical no-swizzle K-major descriptor takes the two 16-byte
 //               K chunks LBO bytes apart, and LBO is simply the distance between the two taps.  Output positions
-//               are linearised over the padded pitch, so every 128-row operand is one uniform-stride run
-//               (SBO = 128 B); the 2p garbage columns per row are discarded by the epilogue.
-//   warp 2      TMEM allocator (512 columns = 32 accumulator slots of 128 x 16, or 8 of 128 x 64).
+//               are linearised over the 128-pixel pitch, so accumulator block b is output row b of the tile and
+//               every 128-row operand is one uniform-stride run (SBO = 128 B); the 2p rightmost columns of a
+//               block are garbage and are discarded by the epilogue.
+//               Warp 1 also owns the TMEM allocation (512 columns = 32 accumulator slots of 128 x 16, or 8 of 128 x 64).
 //   warps 4..   epilogue: tcgen05.ld (lane = pixel, column = output channel), exact requant arithmetic of
 //               SURVEY App. A, 16-byte NHWC16 store (or int8 NCHW + pixel-shuffled fp32 for the last layer).
 // PE semantics: with pe_exact the B operand carries four copies of the weights, each masked to the input
@@ -54,10 +58,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(a), "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -74,9 +78,19 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -96,7 +110,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 constexpr int UMMA_M = 128;
 constexpr int MAX_PAIRS = 13;            // ceil(25 / 2)
 constexpr int TMEM_COLS = 512;
-constexpr int CTRL_WARPS = 4;            // producer, MMA, allocator, spare (keeps epilogue warp % 4 == lane quarter)
+constexpr int CTRL_WARPS = 4;            // warp 0: TMA producer; warps 1-3: MMA issuers (keeps epilogue warp % 4 == lane quarter)
+constexpr int MMA_WARPS = 3;
 
 struct UmmaParams {
   // per-column epilogue constants (column n of the accumulator <-> output channel col_chan[n])
@@ -123,13 +138,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int NPE, int EPI, int EPI_WARPS>
+template <int KS, int NPE, int EPI, int EPI_WARPS>
 __global__ void __launch_bounds__((CTRL_WARPS + EPI_WARPS) * 32, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ UmmaParams P,
                  const uint8_t* __restrict__ w_img, const uint4* __restrict__ shortcut, uint4* __restrict__ out,
                  int8_t* __restrict__ q5, float* __restrict__ y) {
   constexpr int NCOLS = 16 * NPE;
   constexpr int NSLOT = TMEM_COLS / NCOLS;
+  constexpr int NP = (KS * KS + 1) / 2;   // tap pairs = MMAs per accumulator block
   constexpr int NWG = EPI_WARPS / 4;
   static_assert(NSLOT % NWG == 0, "slot ownership must be stable per warpgroup");
 
@@ -154,15 +170,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
     mbar_init(&tile_full[0], 1);
     mbar_init(&tile_full[1], 1);
-    mbar_init(&tile_empty[0], 1);
-    mbar_init(&tile_empty[1], 1);
+    mbar_init(&tile_empty[0], MMA_WARPS);
+    mbar_init(&tile_empty[1], MMA_WARPS);
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);          // one elected arrival per epilogue warp of the owning warpgroup
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_base_s, TMEM_COLS);
+  if (warp == 1) tmem_alloc(tmem_base_s, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -181,35 +197,53 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const int r = t - b * tiles_per_frame;
         const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
         mbar_arrive_expect_tx(&tile_full[st], P.box_bytes);
-        tma_load_4d(tile[st], &tmap, 0, tx * P.TW - P.pad, ty * P.TH - P.pad, b, &tile_full[st]);
+        tma_load_3d(tile[st], &tmap, (tx * P.TW - P.pad) * 2, ty * P.TH - P.pad, b, &tile_full[st]);
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t w_addr = smem_u32(w_s);
-      int it = 0;
-      uint32_t g = 0;                       // running accumulator-block counter of this CTA
-      for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
-        const int st = it & 1;
-        mbar_wait(&tile_full[st], (it >> 1) & 1);
+  } else if (warp < CTRL_WARPS) {
+    // ================= MMA issuers (warps 1..3) =================
+    // Accumulator blocks are dealt round-robin to the three issuing warps; MMAs of different blocks are
+    // independent (distinct TMEM columns), so no ordering between the warps is needed.  Descriptors are
+    // kept in registers: per MMA the only arithmetic is one add on the low word (start-address field).
+    const int mw = warp - 1;
+    const bool leader = elect_one();
+    uint32_t a_lo[NP], b_lo[NP];
+    const uint32_t w_addr = smem_u32(w_s);
+#pragma unroll
+    for (int pr = 0; pr < NP; ++pr) {
+      a_lo[pr] = (uint32_t)P.pair_off[pr] | ((uint32_t)P.pair_lbo[pr] << 16);                 // 16-byte units
+      b_lo[pr] = (((w_addr + (uint32_t)pr * (2u * NCOLS * 16u)) & 0x3FFFFu) >> 4) | ((uint32_t)NCOLS << 16);
+    }
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);       // SBO = 128 B, descriptor version 1, no swizzle
+    const uint32_t idesc = P.idesc;
+    int it = 0;
+    uint32_t g0 = 0;
+    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
+      const int st = it & 1;
+      mbar_wait(&tile_full[st], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t a_base = (smem_u32(tile[st]) & 0x3FFFFu) >> 4;
+      for (int mb = mw; mb < P.nblk; mb += MMA_WARPS) {
+        const uint32_t g = g0 + mb;
+        const uint32_t slot = g % NSLOT;
+        mbar_wait(&acc_empty[slot], ((g / NSLOT) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(tile[st]);
-        for (int mb = 0; mb < P.nblk; ++mb, ++g) {
-          const uint32_t slot = g % NSLOT;
-          mbar_wait(&acc_empty[slot], ((g / NSLOT) & 1) ^ 1);
-          tc_fence_after();
+        if (leader) {
           const uint32_t d = tmem_base + slot * NCOLS;
-          for (int pr = 0; pr < P.n_pairs; ++pr) {
-            const uint64_t ad = make_desc(a_base + (uint32_t)(mb * UMMA_M + P.pair_off[pr]) * 16u,
-                                          (uint32_t)P.pair_lbo[pr] * 16u, 128u);
-            const uint64_t bd = make_desc(w_addr + (uint32_t)pr * (2u * NCOLS * 16u), NCOLS * 16u, 128u);
-            umma_i8(d, ad, bd, P.idesc, pr > 0 ? 1u : 0u);
+          const uint32_t row = a_base + (uint32_t)mb * (UMMA_M * 16 / 16);
+#pragma unroll
+          for (int pr = 0; pr < NP; ++pr) {
+            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo[pr] + row);
+            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)b_lo[pr];
+            umma_i8(d, ad, bd, idesc, pr > 0 ? 1u : 0u);
           }
-          umma_commit(&acc_full[slot]);     // implies tcgen05.fence::before_thread_sync
+          umma_commit(&acc_full[slot]);       // implies tcgen05.fence::before_thread_sync
         }
-        umma_commit(&tile_empty[st]);       // the tile buffer is free once every MMA that reads it has retired
+        __syncwarp();
       }
+      if (leader) umma_commit(&tile_empty[st]);   // this warp's MMAs on the tile have retired when it fires
+      __syncwarp();
+      g0 += P.nblk;
     }
   } else if (warp >= CTRL_WARPS) {
     // ================= epilogue =================
@@ -227,10 +261,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const uint32_t g = g0 + mb;
         if ((int)(g % NWG) != wg) continue;
         const uint32_t slot = g % NSLOT;
-        const int L = mb * UMMA_M + quarter * 32 + lane;
-        const int oy = L / P.pitch, ox = L - oy * P.pitch;
+        const int oy = mb, ox = quarter * 32 + lane;       // pitch == UMMA_M: block b is output row b
         const int gy = y0 + oy, gx = x0 + ox;
-        const bool valid = (ox < P.TW) && (oy < P.TH) && (gy < P.H) && (gx < P.W);
+        const bool valid = (ox < P.TW) && (gy < P.H) && (gx < P.W);
         const long long pix = (long long)b * HW + (long long)gy * P.W + gx;
         uint4 sc = make_uint4(0u, 0u, 0u, 0u);
         if (EPI == EPI_RESIDUAL && valid) sc = __ldg(shortcut + pix);
@@ -298,7 +331,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -364,10 +397,10 @@ int umma_prepare_layer(LayerDev& L, const int8_t* w) {
   return SESRQ_OK;
 }
 
-template <int NPE, int EPI, int EPI_WARPS>
+template <int KS, int NPE, int EPI, int EPI_WARPS>
 static int launch_one(const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L, const uint8_t* d_shortcut,
                       uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem, cudaStream_t st) {
-  auto kern = conv_umma_kernel<NPE, EPI, EPI_WARPS>;
+  auto kern = conv_umma_kernel<KS, NPE, EPI, EPI_WARPS>;
   static bool attr_set = false;
   if (!attr_set) {
     SESRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -392,22 +425,20 @@ int launch_conv_umma(const LayerDev& L, const float* /*d_x*/, const uint8_t* d_i
   // ---- tiling ----
   UmmaParams P;
   memset(&P, 0, sizeof(P));
-  const int max_tw = 256 - 2 * pad;
-  P.tiles_x = cdiv(W, std::min(W, 240 > max_tw ? max_tw : 240));
+  P.pitch = UMMA_M;                                                  // 128 px = 2048 B = one TMA box row
+  P.tiles_x = cdiv(W, UMMA_M - 2 * pad);
   P.TW = cdiv(W, P.tiles_x);
-  P.pitch = P.TW + 2 * pad;
   const int taps = c.k * c.k, pairs = (taps + 1) / 2;
   const uint32_t w_bytes = (uint32_t)pairs * 2 * N * 16;
   const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (4 + 2 * (TMEM_COLS / N)) + 64 + 1024;
   const size_t budget = (227 * 1024 - fixed) / 2;                    // per tile stage
-  // rows per tile: as many as fit (<= 32), balanced over the frame
-  int th_max = (int)((budget / 16 - 2 * pad - 128) / P.pitch) - 2 * pad;
+  int th_max = (int)(budget / (UMMA_M * 16)) - 2 * pad - 1;
   th_max = std::max(1, std::min(th_max, 32));
   P.tiles_y = cdiv(H, std::min(H, th_max));
   P.TH = cdiv(H, P.tiles_y);
-  P.nblk = cdiv((P.TH - 1) * P.pitch + P.TW, UMMA_M);
-  P.stage_bytes = (uint32_t)((((size_t)P.nblk * UMMA_M + 2 * pad * P.pitch + 2 * pad) * 16 + 1023) & ~(size_t)1023);
-  P.box_bytes = (uint32_t)((P.TH + 2 * pad) * P.pitch * 16);
+  P.nblk = P.TH;
+  P.stage_bytes = (uint32_t)((((size_t)(P.TH + 2 * pad) * UMMA_M + 2 * pad) * 16 + 1023) & ~(size_t)1023);
+  P.box_bytes = (uint32_t)((P.TH + 2 * pad) * UMMA_M * 16);
   if ((size_t)P.stage_bytes * 2 + fixed > 227 * 1024 || P.TH + 2 * pad > 256) return SESRQ_EUNSUPPORTED;
   P.w_bytes = w_bytes;
   P.num_tiles = P.tiles_x * P.tiles_y * B;
@@ -434,14 +465,14 @@ int launch_conv_umma(const LayerDev& L, const float* /*d_x*/, const uint8_t* d_i
   P.mf = c.mf; P.z_next = c.z_next; P.res_mf = c.res_mf; P.z_res = c.z_res; P.s_out = c.s_out;
   P.relu = c.relu; P.cout = c.cout; P.r_shuffle = c.r_shuffle;
 
-  // ---- tensor map over the NHWC16 input: dims (16 B, W, H, B) ----
+  // ---- tensor map over the NHWC16 input viewed as (W*2 x 8-byte, H, B) ----
   CUtensorMap tmap;
-  cuuint64_t gdim[4] = {16, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t gstr[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-  cuuint32_t box[4] = {16, (cuuint32_t)P.pitch, (cuuint32_t)(P.TH + 2 * pad), 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(d_in), gdim, gstr, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  cuuint64_t gdim[3] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  cuuint32_t box[3] = {(cuuint32_t)UMMA_M * 2, (cuuint32_t)(P.TH + 2 * pad), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t*>(d_in), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
     set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
@@ -454,8 +485,11 @@ int launch_conv_umma(const LayerDev& L, const float* /*d_x*/, const uint8_t* d_i
   const int grid = std::min(P.num_tiles, sms);
   const size_t smem = (size_t)P.stage_bytes * 2 + fixed;
 
-#define SESRQ_UMMA_CASE(NPE_, EPI_, EW_) \
-  return launch_one<NPE_, EPI_, EW_>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st)
+#define SESRQ_UMMA_CASE(NPE_, EPI_, EW_)                                                                   \
+  do {                                                                                                    \
+    if (c.k == 3) return launch_one<3, NPE_, EPI_, EW_>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st); \
+    return launch_one<5, NPE_, EPI_, EW_>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);      \
+  } while (0)
   if (npe == 1) {
     if (c.epi == EPI_PLAIN) SESRQ_UMMA_CASE(1, EPI_PLAIN, 16);
     if (c.epi == EPI_RESIDUAL) SESRQ_UMMA_CASE(1, EPI_RESIDUAL, 16);

@@ -133,6 +133,17 @@ class Int8Net:
         _lib.check(rc, "sesrq_net_forward_i8_host")
         return q5, y
 
+    def profile(self, enable: bool):
+        """Bracket every kernel of forward() with CUDA events (sesrq_net_profile_enable)."""
+        _lib.check(self.lib.sesrq_net_profile_enable(self._h, int(enable)))
+
+    def profile_read(self):
+        """(ms[6], launches[6]) accumulated since the last read; index 5 = input-quantise pass."""
+        ms = (C.c_double * (_lib.NUM_LAYERS + 1))()
+        ln = (C.c_uint64 * (_lib.NUM_LAYERS + 1))()
+        _lib.check(self.lib.sesrq_net_profile_read(self._h, ms, ln))
+        return list(ms), list(ln)
+
     def read_activation(self, domain: int) -> torch.Tensor:
         """q_domain (input.{domain}.pt) of the last forward as int8 NCHW (layer-by-layer parity)."""
         B, H, W = self._ws_shape
