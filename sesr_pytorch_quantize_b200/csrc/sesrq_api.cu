@@ -22,7 +22,7 @@ static const int kNextDomain[SESRQ_NUM_LAYERS] = {1, 2, 3, 1, 5};   // quan_func
 
 // exact range of the per-PE and total partial sums over all codes q in [-128,127]
 static void clamp_bounds(const int8_t* w, int cout, int cin, int k, int acc_bits, int add_bits,
-                         bool* inert_acc, bool* inert_add) {
+                         bool* inert_acc, bool* inert_add, int32_t* risky) {
   const long long lo_acc = -(1LL << (acc_bits - 1)), hi_acc = (1LL << (acc_bits - 1)) - 1;
   const long long lo_add = -(1LL << (add_bits - 1)), hi_add = (1LL << (add_bits - 1)) - 1;
   *inert_acc = true;
@@ -37,8 +37,12 @@ static void clamp_bounds(const int8_t* w, int cout, int cin, int k, int acc_bits
         lo_p[c & 3] += std::min(a, b);
       }
     long long hi = 0, lo = 0;
+    risky[co] = -1;
     for (int p = 0; p < 4; ++p) {
-      if (hi_p[p] > hi_acc || lo_p[p] < lo_acc) *inert_acc = false;
+      if (hi_p[p] > hi_acc || lo_p[p] < lo_acc) {
+        *inert_acc = false;
+        risky[co] = (risky[co] < 0) ? p : 4;
+      }
       hi += hi_p[p];
       lo += lo_p[p];
     }
@@ -194,7 +198,7 @@ int sesrq_net_create(const SesrqNetDesc* d, SesrqNet** out_net) {
     c.lo_add = -(1 << (d->pe_add_bits - 1));
     c.hi_add = (1 << (d->pe_add_bits - 1)) - 1;
     bool inert_acc, inert_add;
-    clamp_bounds(w, l.cout, l.cin, l.ksize, d->pe_acc_bits, d->pe_add_bits, &inert_acc, &inert_add);
+    clamp_bounds(w, l.cout, l.cin, l.ksize, d->pe_acc_bits, d->pe_add_bits, &inert_acc, &inert_add, c.pe_risky);
     c.pe_exact = (inert_acc && inert_add) ? 0 : 1;
     c.epi = (i == 3) ? EPI_RESIDUAL : (i == 4 ? EPI_FINAL : EPI_PLAIN);
     c.relu = l.relu;

@@ -4,23 +4,32 @@
 //   warp 0      TMA producer: one cp.async.bulk.tensor.3d per tile brings a (TH+2p)-row x 128-pixel halo tile of
 //               NHWC16 bytes into shared memory.  The tensor map views a frame row as W*2 8-byte elements so
 //               the box's inner extent is a contiguous 2048-byte run (a 16-byte inner box makes TMA fetch one
-//               32-byte sector per pixel: measured 2x traffic and ~10x slower, profiles/r1a).  Out-of-frame
-//               pixels are zero-filled by TMA, and byte 0 == code -128 == the reference's pad value z'
+//               32-byte sector per pixel: measured 2x traffic, profiles/r1a).  Out-of-frame pixels are
+//               zero-filled by TMA, and byte 0 == code -128 == the reference's pad value z'
 //               (quan_func.py:351-352), so padding is free.
-//   warps 1-3   MMA issuers (accumulator blocks dealt round-robin): one elected thread per warp issues tcgen05.mma.kind::i8 (u8 activations x s8 weights -> s32 in
-//               TMEM).  No im2col: the tile is pixel-major (16 B per pixel), so the A operand of tap (dy,dx)
-//               for 128 consecutive output positions is the same tile shifted by (dy*pitch+dx) pixels.  A K=32
-//               instruction covers two taps: its canonical no-swizzle K-major descriptor takes the two 16-byte
-//               K chunks LBO bytes apart, and LBO is simply the distance between the two taps.  Output positions
-//               are linearised over the 128-pixel pitch, so accumulator block b is output row b of the tile and
-//               every 128-row operand is one uniform-stride run (SBO = 128 B); the 2p rightmost columns of a
-//               block are garbage and are discarded by the epilogue.
-//               Warp 1 also owns the TMEM allocation (512 columns = 32 accumulator slots of 128 x 16, or 8 of 128 x 64).
+//   warps 1-3   MMA issuers (accumulator blocks dealt round-robin): one elected thread per warp issues
+//               tcgen05.mma.kind::i8 (u8 activations x s8 weights -> s32 in TMEM).  No im2col: the tile is
+//               pixel-major (16 B per pixel), so the A operand of tap (dy,dx) for 128 consecutive output
+//               positions is the same tile shifted by (dy*128+dx) pixels.  A K=32 instruction covers two taps:
+//               its canonical no-swizzle K-major descriptor takes the two 16-byte K chunks LBO bytes apart, and
+//               LBO is simply the distance between the two taps.  The tile pitch is 128 pixels, so accumulator
+//               block b is output row b of the tile and every 128-row operand is one uniform-stride run
+//               (SBO = 128 B); the 2p rightmost columns of a block are garbage and the epilogue drops them.
+//               Descriptors live in registers: per MMA the only arithmetic is one add on the low word.
+//               Warp 1 also owns the TMEM allocation (512 columns).
 //   warps 4..   epilogue: tcgen05.ld (lane = pixel, column = output channel), exact requant arithmetic of
-//               SURVEY App. A, 16-byte NHWC16 store (or int8 NCHW + pixel-shuffled fp32 for the last layer).
-// PE semantics: with pe_exact the B operand carries four copies of the weights, each masked to the input
-// channels of one PE (N = 64), so the four per-PE partial sums land in separate TMEM columns and are clamped
-// to PE_ACC_BIT individually before the adder tree -- same instruction count, the tensor pipe has the headroom.
+//               SURVEY App. A, one 16-byte NHWC16 store per pixel (or int8 NCHW + pixel-shuffled fp32 vector
+//               stores for the last layer).
+//
+// PE semantics (quan_func.py:338-370: each of the 4 PEs clamps its partial sum to PE_ACC_BIT before the adder
+// tree).  The host proves per (output channel, PE) whether that clamp can ever fire (exact range of the partial
+// sum over all int8 codes).  Three accumulator layouts, chosen per layer:
+//   NS = 1  no clamp can fire: one 128x16 accumulator, the clamps are skipped.
+//   NS = 2  at most one PE per channel can clamp (x2 conv_last: 2 of 48 pairs): 128x32.  Columns 0-15 hold the
+//           full sums, column 16+n the partial sum of channel n's one risky PE (B rows masked to that PE's
+//           input channels, zero rows elsewhere); the epilogue adds clamp(v) - v.
+//   NS = 4  anything else: 128x64, four PE-masked copies of the weights, the literal clamp tree.
+// All three issue the same number of MMAs; the tensor pipe has the headroom.
 #include <cuda.h>
 #include <algorithm>
 #include <cstring>
@@ -104,6 +113,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// bytes [a,b,c,d] (a lowest) of the four ints saturated to int8: two I2IP instructions.
+// PTX: cvt.pack.sat.s8.s32.b32 d, x, y, z  ->  d = (z << 16) | (sat8(x) << 8) | sat8(y)
+__device__ __forceinline__ uint32_t pack4_sat_s8(int a, int b, int c, int d) {
+  uint32_t t, r;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(d), "r"(c), "r"(0));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(t));
+  return r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel parameters
 // ------------------------------------------------------------------------------------------------
@@ -114,44 +132,42 @@ constexpr int CTRL_WARPS = 4;            // warp 0: TMA producer; warps 1-3: MMA
 constexpr int MMA_WARPS = 3;
 
 struct UmmaParams {
-  // per-column epilogue constants (column n of the accumulator <-> output channel col_chan[n])
-  int32_t col_const[16];                 // fused_const (fast) or add_const (pe_exact) of that channel
-  int32_t col_pe_corr[4][16];
+  // per-column epilogue constants (column n of the accumulator <-> output channel col_chan(n))
+  int32_t c_fused[16];                   // NS=1: sum_p pe_corr + K
+  int32_t c_sum[16];                     // NS=2: sum_p pe_corr
+  int32_t c_k[16];                       // NS=2/4: K (add const)
+  int32_t c_x[16];                       // NS=2: pe_corr of the channel's risky PE
+  int32_t c_pe[4][16];                   // NS=4: pe_corr per PE
+  uint32_t xmask;                        // NS=2: bit n set <=> channel of column n has a risky PE
   int32_t lo_acc, hi_acc, lo_add, hi_add;
   float mf, z_next, res_mf, z_res, s_out;
-  int32_t relu, cout, r_shuffle;
+  int32_t relu, cout;
   // geometry
-  int32_t B, H, W, TH, TW, pitch, tiles_x, tiles_y, num_tiles, nblk, pad;
+  int32_t B, H, W, TH, TW, tiles_x, tiles_y, num_tiles, pad;
   uint32_t box_bytes, stage_bytes, w_bytes;
-  int32_t n_pairs;
   int32_t pair_off[MAX_PAIRS];           // pixel offset of the first tap of the pair inside the tile
   int32_t pair_lbo[MAX_PAIRS];           // pixel distance to the second tap
   uint32_t idesc;
 };
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout NONE
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-
 // ------------------------------------------------------------------------------------------------
-// the kernel
+// the kernel.  KS: kernel size; NS: accumulator sets (1/2/4, see header); EPI: EpilogueKind; RS: PixelShuffle
+// factor of the final epilogue (1 otherwise); EPI_WARPS: number of epilogue warps.
 // ------------------------------------------------------------------------------------------------
-template <int KS, int NPE, int EPI, int EPI_WARPS>
+template <int KS, int NS, int EPI, int RS, int EPI_WARPS>
 __global__ void __launch_bounds__((CTRL_WARPS + EPI_WARPS) * 32, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ UmmaParams P,
                  const uint8_t* __restrict__ w_img, const uint4* __restrict__ shortcut, uint4* __restrict__ out,
                  int8_t* __restrict__ q5, float* __restrict__ y) {
-  constexpr int NCOLS = 16 * NPE;
+  constexpr int NCOLS = 16 * NS;
   constexpr int NSLOT = TMEM_COLS / NCOLS;
   constexpr int NP = (KS * KS + 1) / 2;   // tap pairs = MMAs per accumulator block
   constexpr int NWG = EPI_WARPS / 4;
   static_assert(NSLOT % NWG == 0, "slot ownership must be stable per warpgroup");
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* tile[2] = {smem, smem + P.stage_bytes};
-  uint8_t* w_s = smem + 2 * (size_t)P.stage_bytes;
+  uint8_t* const tile0 = smem;
+  uint8_t* const w_s = smem + 2 * (size_t)P.stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + ((P.w_bytes + 127) & ~127u));
   uint64_t* tile_full = bars;              // [2]
   uint64_t* tile_empty = bars + 2;         // [2]
@@ -197,14 +213,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const int r = t - b * tiles_per_frame;
         const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
         mbar_arrive_expect_tx(&tile_full[st], P.box_bytes);
-        tma_load_3d(tile[st], &tmap, (tx * P.TW - P.pad) * 2, ty * P.TH - P.pad, b, &tile_full[st]);
+        tma_load_3d(tile0 + (size_t)st * P.stage_bytes, &tmap, (tx * P.TW - P.pad) * 2, ty * P.TH - P.pad, b, &tile_full[st]);
       }
     }
   } else if (warp < CTRL_WARPS) {
     // ================= MMA issuers (warps 1..3) =================
-    // Accumulator blocks are dealt round-robin to the three issuing warps; MMAs of different blocks are
-    // independent (distinct TMEM columns), so no ordering between the warps is needed.  Descriptors are
-    // kept in registers: per MMA the only arithmetic is one add on the low word (start-address field).
     const int mw = warp - 1;
     const bool leader = elect_one();
     uint32_t a_lo[NP], b_lo[NP];
@@ -214,16 +227,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       a_lo[pr] = (uint32_t)P.pair_off[pr] | ((uint32_t)P.pair_lbo[pr] << 16);                 // 16-byte units
       b_lo[pr] = (((w_addr + (uint32_t)pr * (2u * NCOLS * 16u)) & 0x3FFFFu) >> 4) | ((uint32_t)NCOLS << 16);
     }
-    const uint32_t desc_hi = (128u >> 4) | (1u << 14);       // SBO = 128 B, descriptor version 1, no swizzle
+    // cute::UMMA::SmemDescriptor high word: SBO = 128 B (bits 32-45), version 1 (bit 46), no swizzle
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
     const uint32_t idesc = P.idesc;
+    const uint32_t tile_addr0 = (smem_u32(tile0) & 0x3FFFFu) >> 4;
     int it = 0;
     uint32_t g0 = 0;
     for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
       const int st = it & 1;
+      const int r = t % tiles_per_frame;
+      const int nblk = min(P.TH, P.H - (r / P.tiles_x) * P.TH);     // rows of this tile that exist
       mbar_wait(&tile_full[st], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t a_base = (smem_u32(tile[st]) & 0x3FFFFu) >> 4;
-      for (int mb = mw; mb < P.nblk; mb += MMA_WARPS) {
+      const uint32_t a_base = tile_addr0 + (uint32_t)st * (P.stage_bytes >> 4);
+      for (int mb = mw; mb < nblk; mb += MMA_WARPS) {
         const uint32_t g = g0 + mb;
         const uint32_t slot = g % NSLOT;
         mbar_wait(&acc_empty[slot], ((g / NSLOT) & 1) ^ 1);
@@ -241,90 +258,119 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         }
         __syncwarp();
       }
-      if (leader) umma_commit(&tile_empty[st]);   // this warp's MMAs on the tile have retired when it fires
+      if (leader) umma_commit(&tile_empty[st]);   // fires when this warp's MMAs on the tile have retired
       __syncwarp();
-      g0 += P.nblk;
+      g0 += nblk;
     }
-  } else if (warp >= CTRL_WARPS) {
+  } else {
     // ================= epilogue =================
-    const int ew = warp - CTRL_WARPS;
-    const int wg = ew >> 2;                 // warpgroup
-    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const int wg = (warp - CTRL_WARPS) >> 2;      // warpgroup
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int ox = quarter * 32 + lane;           // pitch == UMMA_M: block b is output row b, lane is the column
     const long long HW = (long long)P.H * P.W;
-    uint32_t g0 = 0;                        // accumulator-block counter at the start of the current tile
+    const float relu_floor = P.relu ? 0.f : -INFINITY;
+    uint32_t g0 = 0;
     for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
       const int b = t / tiles_per_frame;
       const int r = t - b * tiles_per_frame;
       const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
-      const int y0 = ty * P.TH, x0 = tx * P.TW;
-      for (int mb = 0; mb < P.nblk; ++mb) {
+      const int y0 = ty * P.TH, gx = tx * P.TW + ox;
+      const int nblk = min(P.TH, P.H - y0);
+      const bool valid = (ox < P.TW) && (gx < P.W);
+      const long long pix0 = (long long)b * HW + (long long)y0 * P.W + gx;
+      const int first = (int)((wg + NWG - (g0 % NWG)) % NWG);
+      for (int mb = first; mb < nblk; mb += NWG) {
         const uint32_t g = g0 + mb;
-        if ((int)(g % NWG) != wg) continue;
         const uint32_t slot = g % NSLOT;
-        const int oy = mb, ox = quarter * 32 + lane;       // pitch == UMMA_M: block b is output row b
-        const int gy = y0 + oy, gx = x0 + ox;
-        const bool valid = (ox < P.TW) && (gy < P.H) && (gx < P.W);
-        const long long pix = (long long)b * HW + (long long)gy * P.W + gx;
+        const long long pix = pix0 + (long long)mb * P.W;
         uint4 sc = make_uint4(0u, 0u, 0u, 0u);
         if (EPI == EPI_RESIDUAL && valid) sc = __ldg(shortcut + pix);
 
         __syncwarp();                        // the .sync.aligned TMEM loads below need a converged warp
         mbar_wait(&acc_full[slot], (g / NSLOT) & 1);
         tc_fence_after();
-        int acc[NPE][16];
+        int acc[NS][16];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * NCOLS;
 #pragma unroll
-        for (int p = 0; p < NPE; ++p) tmem_ld16(taddr + p * 16, acc[p]);
+        for (int p = 0; p < NS; ++p) tmem_ld16(taddr + p * 16, acc[p]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[slot]);
 
         if (valid) {
-        const uint32_t scw[4] = {sc.x, sc.y, sc.z, sc.w};
-        uint32_t ow[4] = {0u, 0u, 0u, 0u};
+          // ---- A = clampAdd(sum_p clampAcc(P_p)) + K  (quan_func.py:370,437,491) ----
+          int A[16];
 #pragma unroll
-        for (int n = 0; n < 16; ++n) {
-          int A;
-          if (NPE == 1) {
-            A = acc[0][n] + P.col_const[n];
-          } else {
-            int s = 0;
+          for (int n = 0; n < 16; ++n) {
+            if (NS == 1) {
+              A[n] = acc[0][n] + P.c_fused[n];
+            } else if (NS == 2) {
+              int s = acc[0][n] + P.c_sum[n];
+              if (P.xmask & (1u << n)) {
+                const int v = acc[NS - 1][n] + P.c_x[n];
+                s += clampi(v, P.lo_acc, P.hi_acc) - v;
+              }
+              A[n] = clampi(s, P.lo_add, P.hi_add) + P.c_k[n];
+            } else {
+              int s = 0;
 #pragma unroll
-            for (int p = 0; p < NPE; ++p) s += clampi(acc[p][n] + P.col_pe_corr[p][n], P.lo_acc, P.hi_acc);
-            A = clampi(s, P.lo_add, P.hi_add) + P.col_const[n];
+              for (int p = 0; p < NS; ++p) s += clampi(acc[p][n] + P.c_pe[p][n], P.lo_acc, P.hi_acc);
+              A[n] = clampi(s, P.lo_add, P.hi_add) + P.c_k[n];
+            }
           }
-          const float yv = requant(A, P.mf);
           if (EPI == EPI_FINAL) {
-            if (n < P.cout) {               // columns are in natural channel order for the last layer
-              const int q = quant_add_zero(yv, P.z_next);
-              if (q5) q5[((long long)b * P.cout + n) * HW + (long long)gy * P.W + gx] = (int8_t)q;
-              if (y) {
-                const float o = __fmul_rn(__fsub_rn((float)q, P.z_next), P.s_out);
-                const int rr = P.r_shuffle, r2 = rr * rr;
-                const int cc = n / r2, ii = (n % r2) / rr, jj = n % rr;
-                const int Co = P.cout / r2;
-                y[(((long long)b * Co + cc) * (P.H * rr) + (gy * rr + ii)) * (long long)(P.W * rr) + (gx * rr + jj)] = o;
+            // q5 = clamp(rint(y + z5)); out = (q5 - z5) * s5 (:585,:594); columns are in natural channel order
+            constexpr int R2 = RS * RS;
+            const long long HrWr = HW * R2;
+            const int Wr = P.W * RS;
+            const int Co = P.cout / R2;
+            float* yb = y ? y + (long long)b * Co * HrWr + (long long)(y0 + mb) * RS * Wr + (long long)gx * RS : nullptr;
+            int8_t* qb = q5 ? q5 + (long long)b * P.cout * HW + (long long)(y0 + mb) * P.W + gx : nullptr;
+#pragma unroll
+            for (int n0 = 0; n0 < 16; n0 += RS) {
+              if (n0 < P.cout) {
+                float o[RS];
+#pragma unroll
+                for (int j = 0; j < RS; ++j) {
+                  const float yv = requant(A[n0 + j], P.mf);
+                  const int q = min(max(__float2int_rn(__fadd_rn(yv, P.z_next)), -128), 127);
+                  if (qb) qb[(long long)(n0 + j) * HW] = (int8_t)q;
+                  o[j] = __fmul_rn(__fsub_rn((float)q, P.z_next), P.s_out);
+                }
+                if (yb) {
+                  float* dst = yb + (long long)(n0 / R2) * HrWr + (long long)((n0 % R2) / RS) * Wr;
+                  if constexpr (RS == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                  else if constexpr (RS == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
+                  else *dst = o[0];
+                }
               }
             }
           } else {
-            const float a = P.relu ? fmaxf(yv, 0.f) : yv;
-            int v;
-            if (EPI == EPI_RESIDUAL) {
-              const int ic = quant_add_zero(a, -128.f);
-              const int vrc = (scw[n >> 2] >> (8 * (n & 3))) & 0xff;
-              const float tt = __fmul_rn((float)(vrc + ic + 128), P.res_mf);
-              v = quant_add_zero(tt, P.z_res) + 128;
-            } else {
-              v = quant_add_zero(a, P.z_next) + 128;
+            uint32_t ow[4];
+            const uint32_t scw[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              int q[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float a = fmaxf(requant(A[4 * w + j], P.mf), relu_floor);
+                if (EPI == EPI_RESIDUAL) {
+                  const int ic = min(__float2int_rn(__fadd_rn(a, -128.f)), 127);         // :251 (a >= 0)
+                  const int vrc = (int)__byte_perm(scw[w], 0u, 0x4440u + j);              // rc + 128 (:250)
+                  const float tt = __fmul_rn((float)(vrc + ic + 128), P.res_mf);          // :252,:269
+                  q[j] = __float2int_rn(__fadd_rn(tt, P.z_res));                          // :270, clamped by the pack
+                } else {
+                  q[j] = __float2int_rn(__fadd_rn(a, P.z_next));                          // :280, clamped by the pack
+                }
+              }
+              ow[w] = pack4_sat_s8(q[0], q[1], q[2], q[3]) ^ 0x80808080u;                 // v = q + 128
             }
-            ow[n >> 2] |= (uint32_t)v << (8 * (n & 3));
+            out[pix] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
           }
         }
-        if (EPI != EPI_FINAL) out[pix] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        }  // valid
       }
-      g0 += P.nblk;
+      g0 += nblk;
     }
   }
 
@@ -359,16 +405,26 @@ static EncodeTiledFn get_encode_fn() {
 bool umma_supported(const LayerConst& c) {
   // 16 input channels from an NHWC16 tensor whose out-of-frame value is byte 0 (z' == -128);
   // layer 0 (fp32 input, cin < 16) and other zero points run on the generic path.
-  return c.cin == 16 && c.pad_byte == 0 && c.save_rc == 0 && (c.k == 3 || c.k == 5);
+  if (!(c.cin == 16 && c.pad_byte == 0 && c.save_rc == 0 && (c.k == 3 || c.k == 5))) return false;
+  if (c.epi == EPI_FINAL && !(c.r_shuffle == 1 || c.r_shuffle == 2 || c.r_shuffle == 4)) return false;
+  return true;
 }
 
-// B operand image: for every tap pair, [2 K-halves][N/8 row groups][8 rows][16 B]; row n of PE copy p holds
-// the weights of output channel col_chan(n) for the 16 input-channel bytes (masked to word p when pe_exact).
+// Accumulator layout for this layer (see header): 1, 2 or 4 sets of 16 columns.
+static int accumulator_sets(const LayerConst& c) {
+  if (!c.pe_exact) return 1;
+  for (int co = 0; co < c.cout; ++co)
+    if (c.pe_risky[co] > 3) return 4;          // more than one PE of a channel can clamp
+  return 2;
+}
+
+// B operand image: for every tap pair, [2 K-halves][N/8 row groups][8 rows][16 B]; row n of set s holds the
+// weights of output channel col_chan(n) for the 16 input-channel bytes, masked per set as the layout requires.
 int umma_prepare_layer(LayerDev& L, const int8_t* w) {
   const LayerConst& c = L.c;
   const int taps = c.k * c.k, pairs = (taps + 1) / 2;
-  const int npe = c.pe_exact ? 4 : 1;
-  const int N = 16 * npe;
+  const int ns = accumulator_sets(c);
+  const int N = 16 * ns;
   L.umma_n = N;
   std::vector<uint8_t> img((size_t)pairs * 2 * N * 16, 0);
   const bool natural = (c.epi == EPI_FINAL);
@@ -377,14 +433,20 @@ int umma_prepare_layer(LayerDev& L, const int8_t* w) {
       const int t = 2 * pr + h;
       if (t >= taps) continue;
       for (int n = 0; n < N; ++n) {
-        const int p = n / 16, nn = n % 16;
+        const int set = n / 16, nn = n % 16;
         const int co = natural ? nn : chan_of_byte(nn);
         if (co >= c.cout) continue;
+        int only_pe = -1;                      // -1: all PEs
+        if (ns == 4) only_pe = set;
+        if (ns == 2 && set == 1) {
+          if (c.pe_risky[co] < 0) continue;    // no risky PE: zero rows
+          only_pe = c.pe_risky[co];
+        }
         uint8_t* row = img.data() + (((size_t)pr * 2 + h) * N + n) * 16;
         for (int j = 0; j < 16; ++j) {
           const int ci = chan_of_byte(j);
           if (ci >= c.cin) continue;
-          if (npe == 4 && (j >> 2) != p) continue;
+          if (only_pe >= 0 && (j >> 2) != only_pe) continue;
           row[j] = (uint8_t)w[((size_t)co * c.cin + ci) * taps + t];
         }
       }
@@ -397,10 +459,10 @@ int umma_prepare_layer(LayerDev& L, const int8_t* w) {
   return SESRQ_OK;
 }
 
-template <int KS, int NPE, int EPI, int EPI_WARPS>
+template <int KS, int NS, int EPI, int RS, int EPI_WARPS>
 static int launch_one(const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L, const uint8_t* d_shortcut,
                       uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem, cudaStream_t st) {
-  auto kern = conv_umma_kernel<KS, NPE, EPI, EPI_WARPS>;
+  auto kern = conv_umma_kernel<KS, NS, EPI, RS, EPI_WARPS>;
   static bool attr_set = false;
   if (!attr_set) {
     SESRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -412,6 +474,26 @@ static int launch_one(const CUtensorMap& tmap, const UmmaParams& P, const LayerD
   return SESRQ_OK;
 }
 
+template <int KS, int NS, int EPI_WARPS>
+static int launch_epi(const LayerConst& c, const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L,
+                      const uint8_t* d_shortcut, uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem,
+                      cudaStream_t st) {
+  if (c.epi == EPI_PLAIN) return launch_one<KS, NS, EPI_PLAIN, 1, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+  if (c.epi == EPI_RESIDUAL) return launch_one<KS, NS, EPI_RESIDUAL, 1, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+  if (c.r_shuffle == 4) return launch_one<KS, NS, EPI_FINAL, 4, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+  if (c.r_shuffle == 2) return launch_one<KS, NS, EPI_FINAL, 2, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+  return launch_one<KS, NS, EPI_FINAL, 1, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+}
+
+template <int KS>
+static int launch_ns(int ns, const LayerConst& c, const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L,
+                     const uint8_t* d_shortcut, uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem,
+                     cudaStream_t st) {
+  if (ns == 1) return launch_epi<KS, 1, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+  if (ns == 2) return launch_epi<KS, 2, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+  return launch_epi<KS, 4, 8>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+}
+
 int launch_conv_umma(const LayerDev& L, const float* /*d_x*/, const uint8_t* d_in, const uint8_t* d_shortcut,
                      uint8_t* d_out, int8_t* d_q5, float* d_y, int B, int H, int W, cudaStream_t st) {
   const LayerConst& c = L.c;
@@ -419,13 +501,12 @@ int launch_conv_umma(const LayerDev& L, const float* /*d_x*/, const uint8_t* d_i
   if (!encode) return SESRQ_EUNSUPPORTED;
   if (!d_in) return SESRQ_EINVAL;
   const int pad = c.pad;
-  const int npe = c.pe_exact ? 4 : 1;
-  const int N = 16 * npe;
+  const int ns = L.umma_n / 16;
+  const int N = L.umma_n;
 
-  // ---- tiling ----
+  // ---- tiling: 128-pixel pitch (one TMA box row = 2048 B), TH output rows per tile ----
   UmmaParams P;
   memset(&P, 0, sizeof(P));
-  P.pitch = UMMA_M;                                                  // 128 px = 2048 B = one TMA box row
   P.tiles_x = cdiv(W, UMMA_M - 2 * pad);
   P.TW = cdiv(W, P.tiles_x);
   const int taps = c.k * c.k, pairs = (taps + 1) / 2;
@@ -436,18 +517,16 @@ int launch_conv_umma(const LayerDev& L, const float* /*d_x*/, const uint8_t* d_i
   th_max = std::max(1, std::min(th_max, 32));
   P.tiles_y = cdiv(H, std::min(H, th_max));
   P.TH = cdiv(H, P.tiles_y);
-  P.nblk = P.TH;
   P.stage_bytes = (uint32_t)((((size_t)(P.TH + 2 * pad) * UMMA_M + 2 * pad) * 16 + 1023) & ~(size_t)1023);
   P.box_bytes = (uint32_t)((P.TH + 2 * pad) * UMMA_M * 16);
   if ((size_t)P.stage_bytes * 2 + fixed > 227 * 1024 || P.TH + 2 * pad > 256) return SESRQ_EUNSUPPORTED;
   P.w_bytes = w_bytes;
   P.num_tiles = P.tiles_x * P.tiles_y * B;
   P.B = B; P.H = H; P.W = W; P.pad = pad;
-  P.n_pairs = pairs;
   for (int pr = 0; pr < pairs; ++pr) {
     const int t0 = 2 * pr, t1 = 2 * pr + 1;
-    const int o0 = (t0 / c.k) * P.pitch + (t0 % c.k);
-    const int o1 = (t1 < taps) ? (t1 / c.k) * P.pitch + (t1 % c.k) : o0 + 1;   // dummy half: weights are zero
+    const int o0 = (t0 / c.k) * UMMA_M + (t0 % c.k);
+    const int o1 = (t1 < taps) ? (t1 / c.k) * UMMA_M + (t1 % c.k) : o0 + 1;   // dummy half: weights are zero
     P.pair_off[pr] = o0;
     P.pair_lbo[pr] = o1 - o0;
   }
@@ -456,14 +535,23 @@ int launch_conv_umma(const LayerDev& L, const float* /*d_x*/, const uint8_t* d_i
   const bool natural = (c.epi == EPI_FINAL);
   for (int n = 0; n < 16; ++n) {
     const int co = natural ? n : chan_of_byte(n);
-    if (co < c.cout) {
-      P.col_const[n] = c.pe_exact ? c.add_const[co] : c.fused_const[co];
-      for (int p = 0; p < 4; ++p) P.col_pe_corr[p][n] = c.pe_corr[p][co];
+    if (co >= c.cout) continue;
+    P.c_fused[n] = c.fused_const[co];
+    P.c_k[n] = c.add_const[co];
+    int sum = 0;
+    for (int p = 0; p < 4; ++p) {
+      P.c_pe[p][n] = c.pe_corr[p][co];
+      sum += c.pe_corr[p][co];
+    }
+    P.c_sum[n] = sum;
+    if (ns == 2 && c.pe_risky[co] >= 0) {
+      P.c_x[n] = c.pe_corr[c.pe_risky[co]][co];
+      P.xmask |= 1u << n;
     }
   }
   P.lo_acc = c.lo_acc; P.hi_acc = c.hi_acc; P.lo_add = c.lo_add; P.hi_add = c.hi_add;
   P.mf = c.mf; P.z_next = c.z_next; P.res_mf = c.res_mf; P.z_res = c.z_res; P.s_out = c.s_out;
-  P.relu = c.relu; P.cout = c.cout; P.r_shuffle = c.r_shuffle;
+  P.relu = c.relu; P.cout = c.cout;
 
   // ---- tensor map over the NHWC16 input viewed as (W*2 x 8-byte, H, B) ----
   CUtensorMap tmap;
@@ -484,22 +572,8 @@ int launch_conv_umma(const LayerDev& L, const float* /*d_x*/, const uint8_t* d_i
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(P.num_tiles, sms);
   const size_t smem = (size_t)P.stage_bytes * 2 + fixed;
-
-#define SESRQ_UMMA_CASE(NPE_, EPI_, EW_)                                                                   \
-  do {                                                                                                    \
-    if (c.k == 3) return launch_one<3, NPE_, EPI_, EW_>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st); \
-    return launch_one<5, NPE_, EPI_, EW_>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);      \
-  } while (0)
-  if (npe == 1) {
-    if (c.epi == EPI_PLAIN) SESRQ_UMMA_CASE(1, EPI_PLAIN, 16);
-    if (c.epi == EPI_RESIDUAL) SESRQ_UMMA_CASE(1, EPI_RESIDUAL, 16);
-    SESRQ_UMMA_CASE(1, EPI_FINAL, 16);
-  } else {
-    if (c.epi == EPI_PLAIN) SESRQ_UMMA_CASE(4, EPI_PLAIN, 8);
-    if (c.epi == EPI_RESIDUAL) SESRQ_UMMA_CASE(4, EPI_RESIDUAL, 8);
-    SESRQ_UMMA_CASE(4, EPI_FINAL, 8);
-  }
-#undef SESRQ_UMMA_CASE
+  if (c.k == 3) return launch_ns<3>(ns, c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+  return launch_ns<5>(ns, c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
 }
 
 }  // namespace sesrq
