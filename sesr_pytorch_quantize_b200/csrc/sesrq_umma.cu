@@ -148,7 +148,86 @@ struct UmmaParams {
   int32_t pair_off[MAX_PAIRS];           // pixel offset of the first tap of the pair inside the tile
   int32_t pair_lbo[MAX_PAIRS];           // pixel distance to the second tap
   uint32_t idesc;
+  // layer-0 kernel only
+  int32_t cin;
+  uint32_t pad_word;                     // out-of-frame pixel: byte c = z' + 128 for c < cin
+  float in_scale, in_zero;
 };
+
+// ------------------------------------------------------------------------------------------------
+// epilogue of one output pixel: 16 (x NS) accumulator columns -> codes.  Shared by both kernels.
+// ------------------------------------------------------------------------------------------------
+template <int NS, int EPI, int RS>
+__device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, const int (&acc)[NS][16], const uint4 sc,
+                                               uint4* __restrict__ out_px, int8_t* __restrict__ qb,
+                                               float* __restrict__ yb, const long long HW, const float relu_floor) {
+  // ---- A = clampAdd(sum_p clampAcc(P_p)) + K  (quan_func.py:370,437,491) ----
+  int A[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    if (NS == 1) {
+      A[n] = acc[0][n] + P.c_fused[n];
+    } else if (NS == 2) {
+      int s = acc[0][n] + P.c_sum[n];
+      if (P.xmask & (1u << n)) {
+        const int v = acc[NS - 1][n] + P.c_x[n];
+        s += clampi(v, P.lo_acc, P.hi_acc) - v;
+      }
+      A[n] = clampi(s, P.lo_add, P.hi_add) + P.c_k[n];
+    } else {
+      int s = 0;
+#pragma unroll
+      for (int p = 0; p < NS; ++p) s += clampi(acc[p][n] + P.c_pe[p][n], P.lo_acc, P.hi_acc);
+      A[n] = clampi(s, P.lo_add, P.hi_add) + P.c_k[n];
+    }
+  }
+  if (EPI == EPI_FINAL) {
+    // q5 = clamp(rint(y + z5)); out = (q5 - z5) * s5 (:585,:594); columns are in natural channel order
+    constexpr int R2 = RS * RS;
+    const long long HrWr = HW * R2;
+    const int Wr = P.W * RS;
+#pragma unroll
+    for (int n0 = 0; n0 < 16; n0 += RS) {
+      if (n0 < P.cout) {
+        float o[RS];
+#pragma unroll
+        for (int j = 0; j < RS; ++j) {
+          const float yv = requant(A[n0 + j], P.mf);
+          const int q = min(max(__float2int_rn(__fadd_rn(yv, P.z_next)), -128), 127);
+          if (qb) qb[(long long)(n0 + j) * HW] = (int8_t)q;
+          o[j] = __fmul_rn(__fsub_rn((float)q, P.z_next), P.s_out);
+        }
+        if (yb) {
+          float* dst = yb + (long long)(n0 / R2) * HrWr + (long long)((n0 % R2) / RS) * Wr;
+          if constexpr (RS == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+          else if constexpr (RS == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
+          else *dst = o[0];
+        }
+      }
+    }
+  } else {
+    uint32_t ow[4];
+    const uint32_t scw[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      int q[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = fmaxf(requant(A[4 * w + j], P.mf), relu_floor);
+        if (EPI == EPI_RESIDUAL) {
+          const int ic = min(__float2int_rn(__fadd_rn(a, -128.f)), 127);         // :251 (a >= 0)
+          const int vrc = (int)__byte_perm(scw[w], 0u, 0x4440u + j);              // rc + 128 (:250)
+          const float tt = __fmul_rn((float)(vrc + ic + 128), P.res_mf);          // :252,:269
+          q[j] = __float2int_rn(__fadd_rn(tt, P.z_res));                          // :270, clamped by the pack
+        } else {
+          q[j] = __float2int_rn(__fadd_rn(a, P.z_next));                          // :280, clamped by the pack
+        }
+      }
+      ow[w] = pack4_sat_s8(q[0], q[1], q[2], q[3]) ^ 0x80808080u;                 // v = q + 128
+    }
+    *out_px = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // the kernel.  KS: kernel size; NS: accumulator sets (1/2/4, see header); EPI: EpilogueKind; RS: PixelShuffle
@@ -299,75 +378,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         if (lane == 0) mbar_arrive(&acc_empty[slot]);
 
         if (valid) {
-          // ---- A = clampAdd(sum_p clampAcc(P_p)) + K  (quan_func.py:370,437,491) ----
-          int A[16];
-#pragma unroll
-          for (int n = 0; n < 16; ++n) {
-            if (NS == 1) {
-              A[n] = acc[0][n] + P.c_fused[n];
-            } else if (NS == 2) {
-              int s = acc[0][n] + P.c_sum[n];
-              if (P.xmask & (1u << n)) {
-                const int v = acc[NS - 1][n] + P.c_x[n];
-                s += clampi(v, P.lo_acc, P.hi_acc) - v;
-              }
-              A[n] = clampi(s, P.lo_add, P.hi_add) + P.c_k[n];
-            } else {
-              int s = 0;
-#pragma unroll
-              for (int p = 0; p < NS; ++p) s += clampi(acc[p][n] + P.c_pe[p][n], P.lo_acc, P.hi_acc);
-              A[n] = clampi(s, P.lo_add, P.hi_add) + P.c_k[n];
-            }
-          }
+          float* yb = nullptr;
+          int8_t* qb = nullptr;
           if (EPI == EPI_FINAL) {
-            // q5 = clamp(rint(y + z5)); out = (q5 - z5) * s5 (:585,:594); columns are in natural channel order
             constexpr int R2 = RS * RS;
-            const long long HrWr = HW * R2;
-            const int Wr = P.W * RS;
-            const int Co = P.cout / R2;
-            float* yb = y ? y + (long long)b * Co * HrWr + (long long)(y0 + mb) * RS * Wr + (long long)gx * RS : nullptr;
-            int8_t* qb = q5 ? q5 + (long long)b * P.cout * HW + (long long)(y0 + mb) * P.W + gx : nullptr;
-#pragma unroll
-            for (int n0 = 0; n0 < 16; n0 += RS) {
-              if (n0 < P.cout) {
-                float o[RS];
-#pragma unroll
-                for (int j = 0; j < RS; ++j) {
-                  const float yv = requant(A[n0 + j], P.mf);
-                  const int q = min(max(__float2int_rn(__fadd_rn(yv, P.z_next)), -128), 127);
-                  if (qb) qb[(long long)(n0 + j) * HW] = (int8_t)q;
-                  o[j] = __fmul_rn(__fsub_rn((float)q, P.z_next), P.s_out);
-                }
-                if (yb) {
-                  float* dst = yb + (long long)(n0 / R2) * HrWr + (long long)((n0 % R2) / RS) * Wr;
-                  if constexpr (RS == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-                  else if constexpr (RS == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
-                  else *dst = o[0];
-                }
-              }
-            }
-          } else {
-            uint32_t ow[4];
-            const uint32_t scw[4] = {sc.x, sc.y, sc.z, sc.w};
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              int q[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float a = fmaxf(requant(A[4 * w + j], P.mf), relu_floor);
-                if (EPI == EPI_RESIDUAL) {
-                  const int ic = min(__float2int_rn(__fadd_rn(a, -128.f)), 127);         // :251 (a >= 0)
-                  const int vrc = (int)__byte_perm(scw[w], 0u, 0x4440u + j);              // rc + 128 (:250)
-                  const float tt = __fmul_rn((float)(vrc + ic + 128), P.res_mf);          // :252,:269
-                  q[j] = __float2int_rn(__fadd_rn(tt, P.z_res));                          // :270, clamped by the pack
-                } else {
-                  q[j] = __float2int_rn(__fadd_rn(a, P.z_next));                          // :280, clamped by the pack
-                }
-              }
-              ow[w] = pack4_sat_s8(q[0], q[1], q[2], q[3]) ^ 0x80808080u;                 // v = q + 128
-            }
-            out[pix] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            if (y) yb = y + (long long)b * (P.cout / R2) * (HW * R2) + (long long)(y0 + mb) * RS * (P.W * RS) + (long long)gx * RS;
+            if (q5) qb = q5 + (long long)b * P.cout * HW + (long long)(y0 + mb) * P.W + gx;
           }
+          epilogue_pixel<NS, EPI, RS>(P, acc, sc, out + pix, qb, yb, HW, relu_floor);
         }
       }
       g0 += nblk;
@@ -375,6 +393,200 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   }
 
   // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layer-0 kernel: fp32 NCHW frames with cin <= 4 channels.  Builder warps quantise the halo tile on the fly
+// (clamp(rint(x / s0 + z0)), true fp32 division, quan_func.py:225) into a 4-byte-per-pixel plane S, then
+// expand it into the K-major operand plane  E[row][X] = S[row][X .. X+3]  (16 B per entry).  For output
+// column X and tap row dy, the two 16-byte K chunks of one MMA are E[y+dy][X] (taps dx = 0..3) and
+// E[y+dy][X+4] (dx = 4..7, weights zero beyond the kernel width): LBO = 64 B, SBO = 128 B, one MMA per tap
+// row.  Everything downstream (TMEM accumulators, PE layouts, epilogue) is shared with the 16-channel kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int L0_EP = 132;               // E row pitch in entries (X up to 127 + 4)
+constexpr int L0_SP = 136;               // S row pitch in words  (X + 3 up to 134)
+constexpr int L0_BUILD_WARPS = 8;
+
+template <int KS, int NS, int EPI_WARPS>
+__global__ void __launch_bounds__((CTRL_WARPS + EPI_WARPS + L0_BUILD_WARPS) * 32, 1)
+conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restrict__ w_img,
+                    const float* __restrict__ x, uint4* __restrict__ out) {
+  constexpr int NCOLS = 16 * NS;
+  constexpr int NSLOT = TMEM_COLS / NCOLS;
+  constexpr int NWG = EPI_WARPS / 4;
+  constexpr int PAD = (KS - 1) / 2;
+  static_assert(NSLOT % NWG == 0, "slot ownership must be stable per warpgroup");
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* const e0 = smem;                                         // E planes: 2 stages of stage_bytes
+  uint32_t* const s_plane = reinterpret_cast<uint32_t*>(smem + 2 * (size_t)P.stage_bytes);
+  const uint32_t s_bytes = (uint32_t)(((P.TH + 2 * PAD) * L0_SP * 4 + 127) & ~127);
+  uint8_t* const w_s = smem + 2 * (size_t)P.stage_bytes + s_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + ((P.w_bytes + 127) & ~127u));
+  uint64_t* e_full = bars;                 // [2] count = builder warps
+  uint64_t* e_empty = bars + 2;            // [2] count = MMA warps (tcgen05.commit)
+  uint64_t* acc_full = bars + 4;
+  uint64_t* acc_empty = bars + 4 + NSLOT;
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 4 + 2 * NSLOT);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  for (uint32_t i = threadIdx.x; i < P.w_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(w_img) + i);
+  fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    mbar_init(&e_full[0], L0_BUILD_WARPS);
+    mbar_init(&e_full[1], L0_BUILD_WARPS);
+    mbar_init(&e_empty[0], MMA_WARPS);
+    mbar_init(&e_empty[1], MMA_WARPS);
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_s, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+  const int tiles_per_frame = P.tiles_x * P.tiles_y;
+  const long long HW = (long long)P.H * P.W;
+
+  if (warp == 0) {
+    // idle (no TMA in this kernel: the operand plane is computed, not copied)
+  } else if (warp < CTRL_WARPS) {
+    // ================= MMA issuers =================
+    const int mw = warp - 1;
+    const bool leader = elect_one();
+    uint32_t b_lo[KS];
+    const uint32_t w_addr = smem_u32(w_s);
+#pragma unroll
+    for (int dy = 0; dy < KS; ++dy)
+      b_lo[dy] = (((w_addr + (uint32_t)dy * (2u * NCOLS * 16u)) & 0x3FFFFu) >> 4) | ((uint32_t)NCOLS << 16);
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    const uint32_t idesc = P.idesc;
+    const uint32_t e_addr0 = (smem_u32(e0) & 0x3FFFFu) >> 4;
+    int it = 0;
+    uint32_t g0 = 0;
+    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
+      const int st = it & 1;
+      const int r = t % tiles_per_frame;
+      const int nblk = min(P.TH, P.H - (r / P.tiles_x) * P.TH);
+      mbar_wait(&e_full[st], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t a_base = e_addr0 + (uint32_t)st * (P.stage_bytes >> 4);
+      for (int mb = mw; mb < nblk; mb += MMA_WARPS) {
+        const uint32_t g = g0 + mb;
+        const uint32_t slot = g % NSLOT;
+        mbar_wait(&acc_empty[slot], ((g / NSLOT) & 1) ^ 1);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t d = tmem_base + slot * NCOLS;
+#pragma unroll
+          for (int dy = 0; dy < KS; ++dy) {
+            const uint32_t a_lo = (a_base + (uint32_t)(mb + dy) * L0_EP) | (4u << 16);     // LBO = 4 entries = 64 B
+            umma_i8(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo[dy], idesc, dy > 0 ? 1u : 0u);
+          }
+          umma_commit(&acc_full[slot]);
+        }
+        __syncwarp();
+      }
+      if (leader) umma_commit(&e_empty[st]);
+      __syncwarp();
+      g0 += nblk;
+    }
+  } else if (warp < CTRL_WARPS + EPI_WARPS) {
+    // ================= epilogue (identical to the 16-channel kernel, EPI_PLAIN) =================
+    const int wg = (warp - CTRL_WARPS) >> 2;
+    const int quarter = warp & 3;
+    const int ox = quarter * 32 + lane;
+    const float relu_floor = P.relu ? 0.f : -INFINITY;
+    uint32_t g0 = 0;
+    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+      const int b = t / tiles_per_frame;
+      const int r = t - b * tiles_per_frame;
+      const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
+      const int y0 = ty * P.TH, gx = tx * P.TW + ox;
+      const int nblk = min(P.TH, P.H - y0);
+      const bool valid = (ox < P.TW) && (gx < P.W);
+      const long long pix0 = (long long)b * HW + (long long)y0 * P.W + gx;
+      const int first = (int)((wg + NWG - (g0 % NWG)) % NWG);
+      for (int mb = first; mb < nblk; mb += NWG) {
+        const uint32_t g = g0 + mb;
+        const uint32_t slot = g % NSLOT;
+        __syncwarp();
+        mbar_wait(&acc_full[slot], (g / NSLOT) & 1);
+        tc_fence_after();
+        int acc[NS][16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * NCOLS;
+#pragma unroll
+        for (int p = 0; p < NS; ++p) tmem_ld16(taddr + p * 16, acc[p]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[slot]);
+        if (valid)
+          epilogue_pixel<NS, EPI_PLAIN, 1>(P, acc, make_uint4(0u, 0u, 0u, 0u), out + pix0 + (long long)mb * P.W, nullptr,
+                                           nullptr, HW, relu_floor);
+      }
+      g0 += nblk;
+    }
+  } else {
+    // ================= builders =================
+    const int bt = threadIdx.x - (CTRL_WARPS + EPI_WARPS) * 32;       // 0 .. 255
+    constexpr int NB = L0_BUILD_WARPS * 32;
+    const int cin = P.cin;
+    int it = 0;
+    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
+      const int st = it & 1;
+      const int b = t / tiles_per_frame;
+      const int r = t - b * tiles_per_frame;
+      const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
+      const int y0 = ty * P.TH - PAD, x0 = tx * P.TW - PAD;
+      const int rows = min(P.TH, P.H - ty * P.TH) + 2 * PAD;
+      const float* xb = x + (long long)b * cin * HW;
+      // phase A: quantise (rows x 128 pixels) into S; columns 128..135 only feed discarded outputs
+      asm volatile("bar.sync 1, %0;" ::"n"(NB) : "memory");           // previous tile's phase B has drained S
+      for (int i = bt; i < rows * UMMA_M; i += NB) {
+        const int rr = i >> 7, cc = i & (UMMA_M - 1);
+        const int gy = y0 + rr, gx = x0 + cc;
+        uint32_t word = P.pad_word;
+        if (gy >= 0 && gy < P.H && gx >= 0 && gx < P.W) {
+          const float* px = xb + (long long)gy * P.W + gx;
+          word = 0u;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < cin) word |= (uint32_t)(quant_input(__ldg(px + (long long)c * HW), P.in_scale, P.in_zero) + 128) << (8 * c);
+        }
+        s_plane[rr * L0_SP + cc] = word;
+      }
+      if (bt < rows * (L0_SP - UMMA_M)) {                              // tail columns: keep them defined
+        const int rr = bt / (L0_SP - UMMA_M), cc = UMMA_M + bt % (L0_SP - UMMA_M);
+        s_plane[rr * L0_SP + cc] = P.pad_word;
+      }
+      mbar_wait(&e_empty[st], ((it >> 1) & 1) ^ 1);                    // the MMAs that read this E stage have retired
+      asm volatile("bar.sync 1, %0;" ::"n"(NB) : "memory");           // S complete
+      // phase B: E[row][X] = S[row][X .. X+3]
+      uint4* e = reinterpret_cast<uint4*>(e0 + (size_t)st * P.stage_bytes);
+      for (int i = bt; i < rows * L0_EP; i += NB) {
+        const int rr = i / L0_EP, xx = i - rr * L0_EP;
+        const uint32_t* sp = s_plane + rr * L0_SP + xx;
+        e[i] = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+      }
+      fence_proxy_async();                                             // generic-proxy stores -> visible to UMMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&e_full[st]);
+    }
+  }
+
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -402,9 +614,13 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static bool is_l0_layout(const LayerConst& c) { return c.cin <= 4; }
+
 bool umma_supported(const LayerConst& c) {
-  // 16 input channels from an NHWC16 tensor whose out-of-frame value is byte 0 (z' == -128);
-  // layer 0 (fp32 input, cin < 16) and other zero points run on the generic path.
+  // layer 0: fp32 frames with cin <= 4 (any input zero point: the builder writes the pad value itself);
+  // other layers: 16 input channels from an NHWC16 tensor whose out-of-frame value is byte 0 (z' == -128).
+  // Anything else runs on the generic path.
+  if (is_l0_layout(c)) return c.epi == EPI_PLAIN && c.save_rc == 0 && (c.k == 3 || c.k == 5);
   if (!(c.cin == 16 && c.pad_byte == 0 && c.save_rc == 0 && (c.k == 3 || c.k == 5))) return false;
   if (c.epi == EPI_FINAL && !(c.r_shuffle == 1 || c.r_shuffle == 2 || c.r_shuffle == 4)) return false;
   return true;
@@ -420,8 +636,45 @@ static int accumulator_sets(const LayerConst& c) {
 
 // B operand image: for every tap pair, [2 K-halves][N/8 row groups][8 rows][16 B]; row n of set s holds the
 // weights of output channel col_chan(n) for the 16 input-channel bytes, masked per set as the layout requires.
+// Layer-0 image: one K=32 chunk per tap row dy; byte k of half h <-> tap dx = 4h + k/4, input channel k%4
+// (PE p == channel p for cin <= 4).
+static int umma_prepare_layer0(LayerDev& L, const int8_t* w) {
+  const LayerConst& c = L.c;
+  const int ns = accumulator_sets(c);
+  const int N = 16 * ns;
+  L.umma_n = N;
+  std::vector<uint8_t> img((size_t)c.k * 2 * N * 16, 0);
+  for (int dy = 0; dy < c.k; ++dy)
+    for (int h = 0; h < 2; ++h)
+      for (int n = 0; n < N; ++n) {
+        const int set = n / 16, nn = n % 16;
+        const int co = chan_of_byte(nn);
+        if (co >= c.cout) continue;
+        int only_pe = -1;
+        if (ns == 4) only_pe = set;
+        if (ns == 2 && set == 1) {
+          if (c.pe_risky[co] < 0) continue;
+          only_pe = c.pe_risky[co];
+        }
+        uint8_t* row = img.data() + (((size_t)dy * 2 + h) * N + n) * 16;
+        for (int k = 0; k < 16; ++k) {
+          const int dx = 4 * h + k / 4, ci = k % 4;
+          if (dx >= c.k || ci >= c.cin) continue;
+          if (only_pe >= 0 && ci != only_pe) continue;
+          row[k] = (uint8_t)w[(((size_t)co * c.cin + ci) * c.k + dy) * c.k + dx];
+        }
+      }
+  if (cudaMalloc(&L.d_wumma, img.size()) != cudaSuccess ||
+      cudaMemcpy(L.d_wumma, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_cuda_error(cudaGetLastError(), "umma layer-0 weight upload");
+    return SESRQ_ECUDA;
+  }
+  return SESRQ_OK;
+}
+
 int umma_prepare_layer(LayerDev& L, const int8_t* w) {
   const LayerConst& c = L.c;
+  if (is_l0_layout(c)) return umma_prepare_layer0(L, w);
   const int taps = c.k * c.k, pairs = (taps + 1) / 2;
   const int ns = accumulator_sets(c);
   const int N = 16 * ns;
@@ -494,9 +747,94 @@ static int launch_ns(int ns, const LayerConst& c, const CUtensorMap& tmap, const
   return launch_epi<KS, 4, 8>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
 }
 
-int launch_conv_umma(const LayerDev& L, const float* /*d_x*/, const uint8_t* d_in, const uint8_t* d_shortcut,
+static void fill_epilogue_params(UmmaParams& P, const LayerConst& c, int ns) {
+  const bool natural = (c.epi == EPI_FINAL);
+  for (int n = 0; n < 16; ++n) {
+    const int co = natural ? n : chan_of_byte(n);
+    if (co >= c.cout) continue;
+    P.c_fused[n] = c.fused_const[co];
+    P.c_k[n] = c.add_const[co];
+    int sum = 0;
+    for (int p = 0; p < 4; ++p) {
+      P.c_pe[p][n] = c.pe_corr[p][co];
+      sum += c.pe_corr[p][co];
+    }
+    P.c_sum[n] = sum;
+    if (ns == 2 && c.pe_risky[co] >= 0) {
+      P.c_x[n] = c.pe_corr[c.pe_risky[co]][co];
+      P.xmask |= 1u << n;
+    }
+  }
+  P.lo_acc = c.lo_acc; P.hi_acc = c.hi_acc; P.lo_add = c.lo_add; P.hi_add = c.hi_add;
+  P.mf = c.mf; P.z_next = c.z_next; P.res_mf = c.res_mf; P.z_res = c.z_res; P.s_out = c.s_out;
+  P.relu = c.relu; P.cout = c.cout;
+}
+
+template <int KS, int NS, int EPI_WARPS>
+static int launch_l0_one(const UmmaParams& P, const LayerDev& L, const float* d_x, uint8_t* d_out, int grid, size_t smem,
+                         cudaStream_t st) {
+  auto kern = conv_umma_l0_kernel<KS, NS, EPI_WARPS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SESRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  kern<<<grid, (CTRL_WARPS + EPI_WARPS + L0_BUILD_WARPS) * 32, smem, st>>>(P, L.d_wumma, d_x, reinterpret_cast<uint4*>(d_out));
+  SESRQ_LAUNCH_CHECK("conv_umma_l0_kernel");
+  return SESRQ_OK;
+}
+
+static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_out, int B, int H, int W, cudaStream_t st) {
+  const LayerConst& c = L.c;
+  if (!d_x || !d_out) return SESRQ_EINVAL;
+  const int pad = c.pad, ns = L.umma_n / 16, N = L.umma_n;
+  UmmaParams P;
+  memset(&P, 0, sizeof(P));
+  P.tiles_x = cdiv(W, UMMA_M - 2 * pad);
+  P.TW = cdiv(W, P.tiles_x);
+  const uint32_t w_bytes = (uint32_t)c.k * 2 * N * 16;
+  int th = 32;
+  size_t fixed = 0, smem = 0;
+  for (;; --th) {                                                     // largest TH whose two E stages + S fit
+    const size_t stage = (((size_t)(th + 2 * pad) * L0_EP + 8) * 16 + 1023) & ~(size_t)1023;
+    const size_t s_bytes = ((size_t)(th + 2 * pad) * L0_SP * 4 + 127) & ~(size_t)127;
+    fixed = s_bytes + ((w_bytes + 127) & ~127u) + 8 * (4 + 2 * (TMEM_COLS / N)) + 64 + 1024;
+    smem = 2 * stage + fixed;
+    P.stage_bytes = (uint32_t)stage;
+    if (smem <= 227 * 1024 || th == 1) break;
+  }
+  if (smem > 227 * 1024) return SESRQ_EUNSUPPORTED;
+  P.tiles_y = cdiv(H, std::min(H, th));
+  P.TH = cdiv(H, P.tiles_y);
+  P.w_bytes = w_bytes;
+  P.num_tiles = P.tiles_x * P.tiles_y * B;
+  P.B = B; P.H = H; P.W = W; P.pad = pad;
+  P.idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
+  fill_epilogue_params(P, c, ns);
+  P.cin = c.cin;
+  P.pad_word = 0;
+  for (int ci = 0; ci < c.cin; ++ci) P.pad_word |= (uint32_t)c.pad_byte << (8 * ci);
+  P.in_scale = c.in_scale;
+  P.in_zero = c.in_zero;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = std::min(P.num_tiles, sms);
+#define SESRQ_L0_CASE(KS_)                                                                       \
+  do {                                                                                           \
+    if (ns == 1) return launch_l0_one<KS_, 1, 16>(P, L, d_x, d_out, grid, smem, st);             \
+    if (ns == 2) return launch_l0_one<KS_, 2, 16>(P, L, d_x, d_out, grid, smem, st);             \
+    return launch_l0_one<KS_, 4, 8>(P, L, d_x, d_out, grid, smem, st);                           \
+  } while (0)
+  if (c.k == 3) SESRQ_L0_CASE(3);
+  SESRQ_L0_CASE(5);
+#undef SESRQ_L0_CASE
+}
+
+int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, const uint8_t* d_shortcut,
                      uint8_t* d_out, int8_t* d_q5, float* d_y, int B, int H, int W, cudaStream_t st) {
   const LayerConst& c = L.c;
+  if (is_l0_layout(c)) return launch_conv_umma_l0(L, d_x, d_out, B, H, W, st);
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return SESRQ_EUNSUPPORTED;
   if (!d_in) return SESRQ_EINVAL;
@@ -532,26 +870,7 @@ int launch_conv_umma(const LayerDev& L, const float* /*d_x*/, const uint8_t* d_i
   }
   // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32, A = u8, B = s8, K-major both, N, M = 128
   P.idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
-  const bool natural = (c.epi == EPI_FINAL);
-  for (int n = 0; n < 16; ++n) {
-    const int co = natural ? n : chan_of_byte(n);
-    if (co >= c.cout) continue;
-    P.c_fused[n] = c.fused_const[co];
-    P.c_k[n] = c.add_const[co];
-    int sum = 0;
-    for (int p = 0; p < 4; ++p) {
-      P.c_pe[p][n] = c.pe_corr[p][co];
-      sum += c.pe_corr[p][co];
-    }
-    P.c_sum[n] = sum;
-    if (ns == 2 && c.pe_risky[co] >= 0) {
-      P.c_x[n] = c.pe_corr[c.pe_risky[co]][co];
-      P.xmask |= 1u << n;
-    }
-  }
-  P.lo_acc = c.lo_acc; P.hi_acc = c.hi_acc; P.lo_add = c.lo_add; P.hi_add = c.hi_add;
-  P.mf = c.mf; P.z_next = c.z_next; P.res_mf = c.res_mf; P.z_res = c.z_res; P.s_out = c.s_out;
-  P.relu = c.relu; P.cout = c.cout;
+  fill_epilogue_params(P, c, ns);
 
   // ---- tensor map over the NHWC16 input viewed as (W*2 x 8-byte, H, B) ----
   CUtensorMap tmap;
