@@ -555,18 +555,35 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
       const float* xb = x + (long long)b * cin * HW;
       // phase A: quantise (rows x 128 pixels) into S; columns 128..135 only feed discarded outputs
       asm volatile("bar.sync 1, %0;" ::"n"(NB) : "memory");           // previous tile's phase B has drained S
-      for (int i = bt; i < rows * UMMA_M; i += NB) {
-        const int rr = i >> 7, cc = i & (UMMA_M - 1);
-        const int gy = y0 + rr, gx = x0 + cc;
-        uint32_t word = P.pad_word;
-        if (gy >= 0 && gy < P.H && gx >= 0 && gx < P.W) {
-          const float* px = xb + (long long)gy * P.W + gx;
-          word = 0u;
+      // (U pixels x cin loads are issued back to back so the DRAM latency is paid once per batch, not per pixel)
+      constexpr int U = 6;
+      const int npx = rows * UMMA_M;
+      for (int i0 = bt; i0 < npx; i0 += NB * U) {
+        float v[U][4];
+        bool inside[U];
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (c < cin) word |= (uint32_t)(quant_input(__ldg(px + (long long)c * HW), P.in_scale, P.in_zero) + 128) << (8 * c);
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * NB;
+          const int gy = y0 + (i >> 7), gx = x0 + (i & (UMMA_M - 1));
+          inside[u] = (i < npx) && gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
+          const float* px = xb + (long long)gy * P.W + gx;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[u][c] = (inside[u] && c < cin) ? __ldg(px + (long long)c * HW) : 0.f;
         }
-        s_plane[rr * L0_SP + cc] = word;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * NB;
+          if (i < npx) {
+            uint32_t word = P.pad_word;
+            if (inside[u]) {
+              word = 0u;
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (c < cin) word |= (uint32_t)(quant_input(v[u][c], P.in_scale, P.in_zero) + 128) << (8 * c);
+            }
+            s_plane[(i >> 7) * L0_SP + (i & (UMMA_M - 1))] = word;
+          }
+        }
       }
       if (bt < rows * (L0_SP - UMMA_M)) {                              // tail columns: keep them defined
         const int rr = bt / (L0_SP - UMMA_M), cc = UMMA_M + bt % (L0_SP - UMMA_M);
