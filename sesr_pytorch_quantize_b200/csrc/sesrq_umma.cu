@@ -130,6 +130,7 @@ constexpr int MAX_PAIRS = 13;            // ceil(25 / 2)
 constexpr int TMEM_COLS = 512;
 constexpr int CTRL_WARPS = 4;            // warp 0: TMA producer; warps 1-3: MMA issuers (keeps epilogue warp % 4 == lane quarter)
 constexpr int MMA_WARPS = 3;
+constexpr int MAX_STAGES = 4;
 
 struct UmmaParams {
   // per-column epilogue constants (column n of the accumulator <-> output channel col_chan(n))
@@ -145,6 +146,7 @@ struct UmmaParams {
   // geometry
   int32_t B, H, W, TH, TW, tiles_x, tiles_y, num_tiles, pad;
   uint32_t box_bytes, stage_bytes, w_bytes;
+  int32_t stages;                        // tile buffers in flight (2..MAX_STAGES)
   int32_t pair_off[MAX_PAIRS];           // pixel offset of the first tap of the pair inside the tile
   int32_t pair_lbo[MAX_PAIRS];           // pixel distance to the second tap
   uint32_t idesc;
@@ -246,13 +248,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* const tile0 = smem;
-  uint8_t* const w_s = smem + 2 * (size_t)P.stage_bytes;
+  uint8_t* const w_s = smem + (size_t)P.stages * P.stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + ((P.w_bytes + 127) & ~127u));
-  uint64_t* tile_full = bars;              // [2]
-  uint64_t* tile_empty = bars + 2;         // [2]
-  uint64_t* acc_full = bars + 4;           // [NSLOT]
-  uint64_t* acc_empty = bars + 4 + NSLOT;  // [NSLOT]
-  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 4 + 2 * NSLOT);
+  uint64_t* tile_full = bars;                            // [MAX_STAGES]
+  uint64_t* tile_empty = bars + MAX_STAGES;              // [MAX_STAGES]
+  uint64_t* acc_full = bars + 2 * MAX_STAGES;            // [NSLOT]
+  uint64_t* acc_empty = bars + 2 * MAX_STAGES + NSLOT;   // [NSLOT]
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * NSLOT);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -263,10 +265,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   fence_proxy_async();                      // weights were written through the generic proxy, UMMA reads via async proxy
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
-    mbar_init(&tile_full[0], 1);
-    mbar_init(&tile_full[1], 1);
-    mbar_init(&tile_empty[0], MMA_WARPS);
-    mbar_init(&tile_empty[1], MMA_WARPS);
+    for (int i = 0; i < MAX_STAGES; ++i) {
+      mbar_init(&tile_full[i], 1);
+      mbar_init(&tile_empty[i], MMA_WARPS);
+    }
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);          // one elected arrival per epilogue warp of the owning warpgroup
@@ -284,15 +286,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      int it = 0;
-      for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
-        const int st = it & 1;
-        mbar_wait(&tile_empty[st], ((it >> 1) & 1) ^ 1);
+      int st = 0;
+      uint32_t ph = 0;                       // phase parity of the current pass over the stage ring
+      for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+        mbar_wait(&tile_empty[st], ph ^ 1);
         const int b = t / tiles_per_frame;
         const int r = t - b * tiles_per_frame;
         const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
         mbar_arrive_expect_tx(&tile_full[st], P.box_bytes);
         tma_load_3d(tile0 + (size_t)st * P.stage_bytes, &tmap, (tx * P.TW - P.pad) * 2, ty * P.TH - P.pad, b, &tile_full[st]);
+        if (++st == P.stages) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp < CTRL_WARPS) {
@@ -310,13 +313,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);
     const uint32_t idesc = P.idesc;
     const uint32_t tile_addr0 = (smem_u32(tile0) & 0x3FFFFu) >> 4;
-    int it = 0;
+    int st = 0;
+    uint32_t ph = 0;
     uint32_t g0 = 0;
-    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
-      const int st = it & 1;
+    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
       const int r = t % tiles_per_frame;
       const int nblk = min(P.TH, P.H - (r / P.tiles_x) * P.TH);     // rows of this tile that exist
-      mbar_wait(&tile_full[st], (it >> 1) & 1);
+      mbar_wait(&tile_full[st], ph);
       tc_fence_after();
       const uint32_t a_base = tile_addr0 + (uint32_t)st * (P.stage_bytes >> 4);
       for (int mb = mw; mb < nblk; mb += MMA_WARPS) {
@@ -340,6 +343,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       if (leader) umma_commit(&tile_empty[st]);   // fires when this warp's MMAs on the tile have retired
       __syncwarp();
       g0 += nblk;
+      if (++st == P.stages) { st = 0; ph ^= 1; }
     }
   } else {
     // ================= epilogue =================
@@ -413,7 +417,30 @@ constexpr int L0_EP = 132;               // E row pitch in entries (X up to 127 
 constexpr int L0_SP = 136;               // S row pitch in words  (X + 3 up to 134)
 constexpr int L0_BUILD_WARPS = 8;
 
-template <int KS, int NS, int EPI_WARPS>
+// x / s with a hoisted reciprocal.  `rcp` is the Newton-refined reciprocal of s; the three operations are
+// exactly the quotient steps of div.rn.f32's fast path (q0 = x*rcp; e = fma(-s, q0, x); q = fma(rcp, e, q0)),
+// which is correctly rounded whenever neither the operands nor the quotient are near the exponent limits.
+// Tiny |x| (< 2^-100): the code is decided by the zero point, not by the last bit of the quotient.  Huge |x|
+// would overflow the quotient (Inf - Inf = NaN in the residual), so x is first clamped to +-lim with
+// lim / s = 2^40: beyond it the code is saturated whatever the int32 zero point is.  The quantised result is
+// therefore identical to true division for every finite input (tests: rounding-boundary / extreme inputs).
+struct ExactDiv {
+  float s, rcp, lim;
+  __device__ __forceinline__ explicit ExactDiv(float s_) : s(s_) {
+    float y0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(s_));
+    rcp = __fmaf_rn(y0, __fmaf_rn(-s_, y0, 1.0f), y0);
+    lim = fminf(__fmul_rn(s_, 1099511627776.f), 1.2676506e30f);      // min(s * 2^40, 2^100)
+  }
+  __device__ __forceinline__ float operator()(float x) const {
+    x = fminf(fmaxf(x, -lim), lim);
+    const float q0 = __fmul_rn(x, rcp);
+    const float e = __fmaf_rn(-s, q0, x);
+    return __fmaf_rn(rcp, e, q0);
+  }
+};
+
+template <int KS, int NS, int CIN, int EPI_WARPS>
 __global__ void __launch_bounds__((CTRL_WARPS + EPI_WARPS + L0_BUILD_WARPS) * 32, 1)
 conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restrict__ w_img,
                     const float* __restrict__ x, uint4* __restrict__ out) {
@@ -424,16 +451,16 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
   static_assert(NSLOT % NWG == 0, "slot ownership must be stable per warpgroup");
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* const e0 = smem;                                         // E planes: 2 stages of stage_bytes
-  uint32_t* const s_plane = reinterpret_cast<uint32_t*>(smem + 2 * (size_t)P.stage_bytes);
+  uint8_t* const e0 = smem;                                         // E planes: P.stages buffers of stage_bytes
+  uint32_t* const s_plane = reinterpret_cast<uint32_t*>(smem + (size_t)P.stages * P.stage_bytes);
   const uint32_t s_bytes = (uint32_t)(((P.TH + 2 * PAD) * L0_SP * 4 + 127) & ~127);
-  uint8_t* const w_s = smem + 2 * (size_t)P.stage_bytes + s_bytes;
+  uint8_t* const w_s = smem + (size_t)P.stages * P.stage_bytes + s_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + ((P.w_bytes + 127) & ~127u));
-  uint64_t* e_full = bars;                 // [2] count = builder warps
-  uint64_t* e_empty = bars + 2;            // [2] count = MMA warps (tcgen05.commit)
-  uint64_t* acc_full = bars + 4;
-  uint64_t* acc_empty = bars + 4 + NSLOT;
-  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 4 + 2 * NSLOT);
+  uint64_t* e_full = bars;                               // [MAX_STAGES] count = builder warps
+  uint64_t* e_empty = bars + MAX_STAGES;                 // [MAX_STAGES] count = MMA warps (tcgen05.commit)
+  uint64_t* acc_full = bars + 2 * MAX_STAGES;
+  uint64_t* acc_empty = bars + 2 * MAX_STAGES + NSLOT;
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * NSLOT);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -442,10 +469,10 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
     reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(w_img) + i);
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
-    mbar_init(&e_full[0], L0_BUILD_WARPS);
-    mbar_init(&e_full[1], L0_BUILD_WARPS);
-    mbar_init(&e_empty[0], MMA_WARPS);
-    mbar_init(&e_empty[1], MMA_WARPS);
+    for (int i = 0; i < MAX_STAGES; ++i) {
+      mbar_init(&e_full[i], L0_BUILD_WARPS);
+      mbar_init(&e_empty[i], MMA_WARPS);
+    }
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);
@@ -474,13 +501,13 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);
     const uint32_t idesc = P.idesc;
     const uint32_t e_addr0 = (smem_u32(e0) & 0x3FFFFu) >> 4;
-    int it = 0;
+    int st = 0;
+    uint32_t ph = 0;
     uint32_t g0 = 0;
-    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
-      const int st = it & 1;
+    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
       const int r = t % tiles_per_frame;
       const int nblk = min(P.TH, P.H - (r / P.tiles_x) * P.TH);
-      mbar_wait(&e_full[st], (it >> 1) & 1);
+      mbar_wait(&e_full[st], ph);
       tc_fence_after();
       const uint32_t a_base = e_addr0 + (uint32_t)st * (P.stage_bytes >> 4);
       for (int mb = mw; mb < nblk; mb += MMA_WARPS) {
@@ -502,6 +529,7 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
       if (leader) umma_commit(&e_empty[st]);
       __syncwarp();
       g0 += nblk;
+      if (++st == P.stages) { st = 0; ph ^= 1; }
     }
   } else if (warp < CTRL_WARPS + EPI_WARPS) {
     // ================= epilogue (identical to the 16-channel kernel, EPI_PLAIN) =================
@@ -543,23 +571,24 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
     // ================= builders =================
     const int bt = threadIdx.x - (CTRL_WARPS + EPI_WARPS) * 32;       // 0 .. 255
     constexpr int NB = L0_BUILD_WARPS * 32;
-    const int cin = P.cin;
-    int it = 0;
-    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
-      const int st = it & 1;
+    const ExactDiv div_s0(P.in_scale);
+    const float z0 = P.in_zero;
+    int st = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
       const int b = t / tiles_per_frame;
       const int r = t - b * tiles_per_frame;
       const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
       const int y0 = ty * P.TH - PAD, x0 = tx * P.TW - PAD;
       const int rows = min(P.TH, P.H - ty * P.TH) + 2 * PAD;
-      const float* xb = x + (long long)b * cin * HW;
+      const float* xb = x + (long long)b * CIN * HW;
       // phase A: quantise (rows x 128 pixels) into S; columns 128..135 only feed discarded outputs
       asm volatile("bar.sync 1, %0;" ::"n"(NB) : "memory");           // previous tile's phase B has drained S
       // (U pixels x cin loads are issued back to back so the DRAM latency is paid once per batch, not per pixel)
       constexpr int U = 6;
       const int npx = rows * UMMA_M;
       for (int i0 = bt; i0 < npx; i0 += NB * U) {
-        float v[U][4];
+        float v[U][CIN];
         bool inside[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -568,19 +597,16 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
           inside[u] = (i < npx) && gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
           const float* px = xb + (long long)gy * P.W + gx;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) v[u][c] = (inside[u] && c < cin) ? __ldg(px + (long long)c * HW) : 0.f;
+          for (int c = 0; c < CIN; ++c) v[u][c] = inside[u] ? __ldg(px + (long long)c * HW) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int i = i0 + u * NB;
           if (i < npx) {
-            uint32_t word = P.pad_word;
-            if (inside[u]) {
-              word = 0u;
+            int q[4] = {-128, -128, -128, -128};            // unused channels: byte 0 (their weights are zero)
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                if (c < cin) word |= (uint32_t)(quant_input(v[u][c], P.in_scale, P.in_zero) + 128) << (8 * c);
-            }
+            for (int c = 0; c < CIN; ++c) q[c] = __float2int_rn(__fadd_rn(div_s0(v[u][c]), z0));   // :225, clamped by the pack
+            const uint32_t word = inside[u] ? (pack4_sat_s8(q[0], q[1], q[2], q[3]) ^ 0x80808080u) : P.pad_word;
             s_plane[(i >> 7) * L0_SP + (i & (UMMA_M - 1))] = word;
           }
         }
@@ -589,7 +615,7 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
         const int rr = bt / (L0_SP - UMMA_M), cc = UMMA_M + bt % (L0_SP - UMMA_M);
         s_plane[rr * L0_SP + cc] = P.pad_word;
       }
-      mbar_wait(&e_empty[st], ((it >> 1) & 1) ^ 1);                    // the MMAs that read this E stage have retired
+      mbar_wait(&e_empty[st], ph ^ 1);                                 // the MMAs that read this E stage have retired
       asm volatile("bar.sync 1, %0;" ::"n"(NB) : "memory");           // S complete
       // phase B: E[row][X] = S[row][X .. X+3]
       uint4* e = reinterpret_cast<uint4*>(e0 + (size_t)st * P.stage_bytes);
@@ -601,6 +627,7 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
       fence_proxy_async();                                             // generic-proxy stores -> visible to UMMA
       __syncwarp();
       if (lane == 0) mbar_arrive(&e_full[st]);
+      if (++st == P.stages) { st = 0; ph ^= 1; }
     }
   }
 
@@ -764,6 +791,31 @@ static int launch_ns(int ns, const LayerConst& c, const CUtensorMap& tmap, const
   return launch_epi<KS, 4, 8>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
 }
 
+// Tile height and stage count: maximise (SM load balance of the static round-robin schedule) x (halo
+// efficiency), subject to >= 2 (preferably >= 3) tile buffers fitting next to the fixed shared memory.
+struct TilePlan { int TH, tiles_y, stages; };
+static TilePlan choose_tiling(int H, int B, int tiles_x, int pad, size_t row_bytes, size_t slack_bytes,
+                              size_t per_row_extra, size_t fixed, int sms) {
+  TilePlan best{0, 0, 0};
+  double best_score = -1.0;
+  const size_t total = 227 * 1024;
+  for (int th = std::min(H, 32); th >= 1; --th) {
+    const int ty = cdiv(H, th);
+    const int TH = cdiv(H, ty);                       // balanced rows per tile
+    const size_t stage = ((size_t)(TH + 2 * pad) * row_bytes + slack_bytes + 1023) & ~(size_t)1023;
+    const size_t extra = (size_t)(TH + 2 * pad) * per_row_extra + 256;
+    if (fixed + extra + 2 * stage > total) continue;
+    const int stages = (int)std::min<size_t>(MAX_STAGES, (total - fixed - extra) / stage);
+    const long long tiles = (long long)tiles_x * ty * B;
+    const double balance = (double)tiles / ((double)sms * (double)((tiles + sms - 1) / sms));
+    const double halo = 1.0 - 0.3 * (2.0 * pad) / (TH + 2.0 * pad);
+    const double depth = stages >= 3 ? 1.0 : 0.9;
+    const double score = balance * halo * depth;
+    if (score > best_score + 1e-9) { best_score = score; best = {TH, ty, stages}; }
+  }
+  return best;
+}
+
 static void fill_epilogue_params(UmmaParams& P, const LayerConst& c, int ns) {
   const bool natural = (c.epi == EPI_FINAL);
   for (int n = 0; n < 16; ++n) {
@@ -787,10 +839,10 @@ static void fill_epilogue_params(UmmaParams& P, const LayerConst& c, int ns) {
   P.relu = c.relu; P.cout = c.cout;
 }
 
-template <int KS, int NS, int EPI_WARPS>
+template <int KS, int NS, int CIN, int EPI_WARPS>
 static int launch_l0_one(const UmmaParams& P, const LayerDev& L, const float* d_x, uint8_t* d_out, int grid, size_t smem,
                          cudaStream_t st) {
-  auto kern = conv_umma_l0_kernel<KS, NS, EPI_WARPS>;
+  auto kern = conv_umma_l0_kernel<KS, NS, CIN, EPI_WARPS>;
   static bool attr_set = false;
   if (!attr_set) {
     SESRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -810,19 +862,18 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
   P.tiles_x = cdiv(W, UMMA_M - 2 * pad);
   P.TW = cdiv(W, P.tiles_x);
   const uint32_t w_bytes = (uint32_t)c.k * 2 * N * 16;
-  int th = 32;
-  size_t fixed = 0, smem = 0;
-  for (;; --th) {                                                     // largest TH whose two E stages + S fit
-    const size_t stage = (((size_t)(th + 2 * pad) * L0_EP + 8) * 16 + 1023) & ~(size_t)1023;
-    const size_t s_bytes = ((size_t)(th + 2 * pad) * L0_SP * 4 + 127) & ~(size_t)127;
-    fixed = s_bytes + ((w_bytes + 127) & ~127u) + 8 * (4 + 2 * (TMEM_COLS / N)) + 64 + 1024;
-    smem = 2 * stage + fixed;
-    P.stage_bytes = (uint32_t)stage;
-    if (smem <= 227 * 1024 || th == 1) break;
-  }
+  const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (2 * MAX_STAGES + 2 * (TMEM_COLS / N)) + 64 + 1024;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const TilePlan tp = choose_tiling(H, B, P.tiles_x, pad, (size_t)L0_EP * 16, 8 * 16, (size_t)L0_SP * 4, fixed, sms);
+  if (tp.stages < 2) return SESRQ_EUNSUPPORTED;
+  P.TH = tp.TH;
+  P.tiles_y = tp.tiles_y;
+  P.stages = tp.stages;
+  P.stage_bytes = (uint32_t)((((size_t)(P.TH + 2 * pad) * L0_EP + 8) * 16 + 1023) & ~(size_t)1023);
+  const size_t smem = (size_t)P.stages * P.stage_bytes + (((size_t)(P.TH + 2 * pad) * L0_SP * 4 + 127) & ~(size_t)127) + fixed;
   if (smem > 227 * 1024) return SESRQ_EUNSUPPORTED;
-  P.tiles_y = cdiv(H, std::min(H, th));
-  P.TH = cdiv(H, P.tiles_y);
   P.w_bytes = w_bytes;
   P.num_tiles = P.tiles_x * P.tiles_y * B;
   P.B = B; P.H = H; P.W = W; P.pad = pad;
@@ -833,18 +884,23 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
   for (int ci = 0; ci < c.cin; ++ci) P.pad_word |= (uint32_t)c.pad_byte << (8 * ci);
   P.in_scale = c.in_scale;
   P.in_zero = c.in_zero;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(P.num_tiles, sms);
+#define SESRQ_L0_NS(KS_, CIN_)                                                                   \
+  do {                                                                                           \
+    if (ns == 1) return launch_l0_one<KS_, 1, CIN_, 16>(P, L, d_x, d_out, grid, smem, st);       \
+    if (ns == 2) return launch_l0_one<KS_, 2, CIN_, 16>(P, L, d_x, d_out, grid, smem, st);       \
+    return launch_l0_one<KS_, 4, CIN_, 8>(P, L, d_x, d_out, grid, smem, st);                     \
+  } while (0)
 #define SESRQ_L0_CASE(KS_)                                                                       \
   do {                                                                                           \
-    if (ns == 1) return launch_l0_one<KS_, 1, 16>(P, L, d_x, d_out, grid, smem, st);             \
-    if (ns == 2) return launch_l0_one<KS_, 2, 16>(P, L, d_x, d_out, grid, smem, st);             \
-    return launch_l0_one<KS_, 4, 8>(P, L, d_x, d_out, grid, smem, st);                           \
+    if (c.cin == 1) SESRQ_L0_NS(KS_, 1);                                                         \
+    if (c.cin == 2) SESRQ_L0_NS(KS_, 2);                                                         \
+    if (c.cin == 3) SESRQ_L0_NS(KS_, 3);                                                         \
+    SESRQ_L0_NS(KS_, 4);                                                                         \
   } while (0)
   if (c.k == 3) SESRQ_L0_CASE(3);
   SESRQ_L0_CASE(5);
+#undef SESRQ_L0_NS
 #undef SESRQ_L0_CASE
 }
 
@@ -866,15 +922,17 @@ int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, c
   P.TW = cdiv(W, P.tiles_x);
   const int taps = c.k * c.k, pairs = (taps + 1) / 2;
   const uint32_t w_bytes = (uint32_t)pairs * 2 * N * 16;
-  const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (4 + 2 * (TMEM_COLS / N)) + 64 + 1024;
-  const size_t budget = (227 * 1024 - fixed) / 2;                    // per tile stage
-  int th_max = (int)(budget / (UMMA_M * 16)) - 2 * pad - 1;
-  th_max = std::max(1, std::min(th_max, 32));
-  P.tiles_y = cdiv(H, std::min(H, th_max));
-  P.TH = cdiv(H, P.tiles_y);
+  const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (2 * MAX_STAGES + 2 * (TMEM_COLS / N)) + 64 + 1024;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const TilePlan tp = choose_tiling(H, B, P.tiles_x, pad, (size_t)UMMA_M * 16, (size_t)2 * pad * 16, 0, fixed, sms);
+  if (tp.stages < 2) return SESRQ_EUNSUPPORTED;
+  P.TH = tp.TH;
+  P.tiles_y = tp.tiles_y;
+  P.stages = tp.stages;
   P.stage_bytes = (uint32_t)((((size_t)(P.TH + 2 * pad) * UMMA_M + 2 * pad) * 16 + 1023) & ~(size_t)1023);
   P.box_bytes = (uint32_t)((P.TH + 2 * pad) * UMMA_M * 16);
-  if ((size_t)P.stage_bytes * 2 + fixed > 227 * 1024 || P.TH + 2 * pad > 256) return SESRQ_EUNSUPPORTED;
   P.w_bytes = w_bytes;
   P.num_tiles = P.tiles_x * P.tiles_y * B;
   P.B = B; P.H = H; P.W = W; P.pad = pad;
@@ -903,11 +961,8 @@ int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, c
     return SESRQ_ECUDA;
   }
 
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(P.num_tiles, sms);
-  const size_t smem = (size_t)P.stage_bytes * 2 + fixed;
+  const size_t smem = (size_t)P.stage_bytes * P.stages + fixed;
   if (c.k == 3) return launch_ns<3>(ns, c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
   return launch_ns<5>(ns, c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
 }

@@ -98,3 +98,28 @@ def test_chunked_batch_equals_single_frames(impl, monkeypatch):
     for b in range(5):
         q1, y1 = net(x[b:b + 1])
         assert torch.equal(q1, q_all[b:b + 1]) and torch.equal(y1, y_all[b:b + 1])
+
+
+@pytest.mark.parametrize("impl", impl_ids())
+@pytest.mark.parametrize("case", ["x2_fixture", "x4_fixture", "synth_neg"])
+def test_input_quantiser_rounding_boundaries(case, impl):
+    """Layer-0 quantiser is clamp(rint(x / s0 + z0)) with TRUE fp32 division (quan_func.py:225):
+    feed inputs sitting on / next to the half-way points, plus zeros, denormals, huge values and negatives."""
+    g = load_golden(case)
+    cin = g.wf[0].shape[1]
+    s0 = np.float32(g.scales[0])
+    rng = np.random.default_rng(11)
+    H, W = 48, 256
+    k = rng.integers(-40, 300, size=(1, cin, H, W)).astype(np.float32)
+    x = (k + np.float32(0.5)) * s0                                  # half-way points of the code grid
+    ulps = rng.integers(-3, 4, size=x.shape)
+    x = (x.view(np.int32) + ulps.astype(np.int32)).view(np.float32)  # +-3 ulp around them
+    x[0, :, 0, 0:8] = [0.0, -0.0, 1e-45, -1e-40, 1e-38, 3e38, -3e38, 1.0]
+    x[0, :, 1, :] = rng.random((cin, W), dtype=np.float32) * np.float32(1e-30)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    onet = orc.derive_net(g.wf, g.bf, g.scales, g.zeros, g.r, pe_add_bit=g.pe_add_bit)
+    q5_ref, y_ref = orc.forward_int(onet, x)
+    net = build(g, impl)
+    q5, y = net(torch.from_numpy(x).cuda())
+    assert np.array_equal(q5.cpu().numpy(), q5_ref)
+    assert np.array_equal(y.cpu().numpy(), y_ref)
