@@ -138,24 +138,39 @@ def compile_network(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tens
         raise ValueError("the SESR/NRDM hot path has exactly 5 collapsed conv layers")
     if len(scales) != 6 or len(zeros) != 6:
         raise ValueError("need 6 activation domains (input.0 .. input.5)")
+    pairs = [symmetric_weight_codes(w, quan_bits) for w in weights]
+    return compile_from_codes([p[0] for p in pairs], [p[1] for p in pairs], biases, scales, zeros, r_shuffle,
+                              pe_acc_bits, pe_add_bits, bias_bits, quan_bits)
+
+
+def compile_from_codes(codes: Sequence[torch.Tensor], w_scales: Sequence[float], biases: Sequence[torch.Tensor],
+                       scales: Sequence[float], zeros: Sequence[int], r_shuffle: int,
+                       pe_acc_bits: int = PE_ACC_BIT, pe_add_bits: int = PE_ADD_BIT,
+                       bias_bits: int = BIAS_BIT, quan_bits: int = QUAN_BIT) -> CompiledNet:
+    """Same as compile_network for weights that are already integer codes (what a graph holds after
+    myQL.quan_func.quantize_model_weight)."""
+    if len(codes) != 5 or len(biases) != 5 or len(w_scales) != 5:
+        raise ValueError("the SESR/NRDM hot path has exactly 5 collapsed conv layers")
+    if len(scales) != 6 or len(zeros) != 6:
+        raise ValueError("need 6 activation domains (input.0 .. input.5)")
     scales = [float(s) for s in scales]
     zeros = [int(z) for z in zeros]
-    layers = []
     lim = 2 ** (bias_bits - 1)
+    layers = []
     for i in range(5):
-        codes, w_scale = symmetric_weight_codes(weights[i], quan_bits)
-        cout, cin, k, k2 = codes.shape
+        c = codes[i].detach().to("cpu", torch.int8).contiguous()
+        cout, cin, k, k2 = c.shape
         if k != k2 or k not in (3, 5):
             raise ValueError("unsupported kernel size %dx%d" % (k, k2))
+        w_scale = float(w_scales[i])
         b = torch.as_tensor(biases[i], dtype=torch.float32).detach().cpu()
         bq = bias_codes(b, scales[i] * w_scale, bias_bits)
-        wsum = codes.to(torch.int64).sum(dim=(1, 2, 3))
+        wsum = c.to(torch.int64).sum(dim=(1, 2, 3))
         add_const = torch.clamp(bq - wsum * zeros[i], min=-lim, max=lim - 1)
         m16, n = quan_layer_between_const(scales[i] / scales[NEXT_DOMAIN[i]] * w_scale)
-        layers.append(CompiledLayer(ksize=k, cin=cin, cout=cout, relu=(i < 4), weight=codes.contiguous(),
-                                    w_scale=w_scale, bias=b, bias_q=bq,
-                                    add_const=[int(v) for v in add_const.tolist()],
-                                    z_in=zeros[i], m16=m16, shift_n=n))
+        layers.append(CompiledLayer(ksize=k, cin=cin, cout=cout, relu=(i < 4), weight=c, w_scale=w_scale, bias=b,
+                                    bias_q=bq, add_const=[int(v) for v in add_const.tolist()], z_in=zeros[i],
+                                    m16=m16, shift_n=n))
     res_m16, res_n = quan_layer_between_const(scales[1] / scales[4])
     return CompiledNet(layers=layers, scales=scales, zeros=zeros, res_m16=res_m16, res_shift_n=res_n,
                        r_shuffle=int(r_shuffle), pe_acc_bits=pe_acc_bits, pe_add_bits=pe_add_bits,

@@ -1,0 +1,46 @@
+"""Configuration constants of the quantisation flow (mirror of the reference's define.py:1-36: same names,
+same meaning, imported by name by test.py / sim.py / myQL).
+
+Differences from the reference defaults, both deliberate:
+  * the seven *_W_FLG dump switches default to False (the reference ships them True and writes ~432 MB of
+    ./output_pt dumps per 80x960 frame).  The fused CUDA path never materialises those tensors; set a flag
+    to True to get the corresponding reference-format dump from the un-fused per-node path.
+  * COMPAT_FILES (new) keeps the reference's file protocol alive: thresholds are read from / running
+    min-max written to ./output_pt/input/input.{i}.*.pt so that test.py's calibration tail and a later
+    sim.py run find them.  Set it to False to keep all state in memory (myQL.state).
+"""
+MFLAG = 3
+TEST_RAW_ADD_NOISE = False
+
+# only 4 PEs are supported (reference define.py:5)
+PE = 4
+
+QUAN_BIT = 8
+
+BIAS_BIT = 16        # clamp of the quantised bias and of bias_q - z * sum(W)
+PE_ACC_BIT = 18      # per-PE accumulator
+PE_ADD_BIT = 20      # PE adder tree
+
+REQUAN_BIT = 16
+REQUAN_N_MAX = 32
+
+# KL-entropy calibration: the reference left these three as comments ("KL discarded", define.py:16-20);
+# here they configure calib.KLCalibrator.
+USE_KL_CALI = False
+BINS_NUM = 2048
+TGT_BINS_NUM = 128
+
+w_flg_c = False
+
+WEIGHT_W_FLG = w_flg_c and True            # weight hex txt
+INPUT_W_FLG = w_flg_c and True             # input.{i}.pt
+BIAS_W_FLG = w_flg_c and True              # conv.bias.{i}.pt
+BIAS_QUAN_W_FLG = w_flg_c and True         # conv.bias.quan{i}.pt
+OUTPUT_PE_W_FLG = w_flg_c and True         # pe_output{i}_{p}.pt
+OUTPUT_PE_ADD_W_FLG = w_flg_c and True     # pe_add_output{i}.pt
+REQUAN_FACTOR_W_FLG = w_flg_c and True     # requan_{i}_{j}.pt / n_{i}_{j}.pt
+
+WEIGHT_W_HIST_PNG = w_flg_c and False
+INPUT_W_HIST_PNG = w_flg_c and False
+
+COMPAT_FILES = True

@@ -1,0 +1,8 @@
+"""sesr_arch_sim.sesr: 3-channel input, x2 PixelShuffle, integer-sim variant (no AddOp).
+Mirror of the reference's models/sesr_arch_sim.py (same constructor defaults and attribute names)."""
+from models._sesr_family import FiveConvNet
+
+
+class sesr(FiveConvNet):
+    def __init__(self, in_channels=3, out_channels=3, num_channels=16, num_lblocks=3, scaling_factor=2):
+        super().__init__(in_channels, out_channels, num_channels, num_lblocks, scaling_factor, sim=True, shuffle=True)
