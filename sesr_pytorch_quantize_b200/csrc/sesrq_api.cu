@@ -205,6 +205,7 @@ int sesrq_net_create(const SesrqNetDesc* d, SesrqNet** out_net) {
     bool inert_acc, inert_add;
     clamp_bounds(w, l.cout, l.cin, l.ksize, d->pe_acc_bits, d->pe_add_bits, &inert_acc, &inert_add, c.pe_risky);
     c.pe_exact = (inert_acc && inert_add) ? 0 : 1;
+    c.add_inert = inert_add ? 1 : 0;
     c.epi = (i == 3) ? EPI_RESIDUAL : (i == 4 ? EPI_FINAL : EPI_PLAIN);
     c.relu = l.relu;
     c.save_rc = (i == 0 && net->need_rc) ? 1 : 0;

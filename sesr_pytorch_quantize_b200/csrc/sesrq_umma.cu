@@ -32,6 +32,7 @@
 // All three issue the same number of MMAs; the tensor pipe has the headroom.
 #include <cuda.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "sesrq_internal.h"
@@ -112,6 +113,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const int (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const int (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // bytes [a,b,c,d] (a lowest) of the four ints saturated to int8: two I2IP instructions.
 // PTX: cvt.pack.sat.s8.s32.b32 d, x, y, z  ->  d = (z << 16) | (sat8(x) << 8) | sat8(y)
@@ -126,29 +143,59 @@ __device__ __forceinline__ uint32_t pack4_sat_s8(int a, int b, int c, int d) {
 // kernel parameters
 // ------------------------------------------------------------------------------------------------
 constexpr int UMMA_M = 128;
-constexpr int MAX_PAIRS = 13;            // ceil(25 / 2)
 constexpr int TMEM_COLS = 512;
 constexpr int CTRL_WARPS = 4;            // warp 0: TMA producer; warps 1-3: MMA issuers (keeps epilogue warp % 4 == lane quarter)
-constexpr int MMA_WARPS = 3;
 constexpr int MAX_STAGES = 4;
 
+// The accumulator slots in TMEM are not zeroed: the epilogue pre-loads every slot (tcgen05.st) with a per-column
+// constant and every MMA accumulates on top of it.  For the single-sum layouts that constant is
+//     c_fused + 0x4B400000   (c_fused = sum_p pe_corr_p + K, 0x4B400000 = bits of 1.5 * 2^23),
+// so the 32-bit word the epilogue reads back IS the float 12582912 + A (exact for |A| < 2^22), and one FFMA
+//     y = fma(m, mf, -12582912 * mf)
+// yields RN(A * mf): m * mf is exact inside the FMA and 12582912 * mf = 3 * M16 * 2^(22-n) is exactly
+// representable, so there is a single rounding, of the exact product A * M16 * 2^-n -- the reference's
+// RN_f32(A * M16) * 2^-n (quan_func.py:529).  No integer add, no int->float conversion, no separate multiply.
+// output rows per completion group (see mma_issue_tile / epilogue_warps)
+template <int NS> struct GroupRows { static constexpr int value = NS == 1 ? 4 : (NS == 2 ? 2 : 1); };
+
+// Accumulator-slot ring.  A tile of TH = TB * nbw output rows owns TH consecutive row slots starting at a multiple
+// of TH (a short bottom tile leaves its trailing slots unused), so slot addresses inside a band are compile-time
+// offsets and a tile never wraps around the ring.  Band w (rows [w*TB, w*TB+TB) of the tile) is issued by warp 1+w.
+// A band is cut into groups of RG rows, the unit of completion signalling.
+constexpr int TB = 8;
+struct RingPos {                              // slot base and phase parity of the current tile
+  uint32_t base = 0, par = 0;
+  __device__ __forceinline__ void advance(uint32_t th, uint32_t nring) {
+    base += th;
+    if (base == nring) { base = 0; par ^= 1u; }
+  }
+};
+__host__ __device__ __forceinline__ int ring_slots(int nslot, int th) { return (nslot / th) * th; }
+template <int RG>
+__device__ __forceinline__ int tile_groups(int nblk) {         // groups of a tile with nblk rows
+  return (nblk / TB) * (TB / RG) + ((nblk % TB) + RG - 1) / RG;
+}
+
+constexpr int32_t MAGIC_BITS = 0x4B400000;
+constexpr float MAGIC_F = 12582912.f;
+
 struct UmmaParams {
-  // per-column epilogue constants (column n of the accumulator <-> output channel col_chan(n))
-  int32_t c_fused[16];                   // NS=1: sum_p pe_corr + K
-  int32_t c_sum[16];                     // NS=2: sum_p pe_corr
-  int32_t c_k[16];                       // NS=2/4: K (add const)
-  int32_t c_x[16];                       // NS=2: pe_corr of the channel's risky PE
-  int32_t c_pe[4][16];                   // NS=4: pe_corr per PE
-  uint32_t xmask;                        // NS=2: bit n set <=> channel of column n has a risky PE
+  int32_t c_init[4][16];                 // TMEM initial value per accumulator set and column
+  int32_t c_kmagic[16];                  // NS=4: K + MAGIC_BITS (added after the clamp tree)
+  int32_t n_risky;                       // NS=2: number of (channel, PE) pairs whose 18-bit clamp can fire
+  int32_t risky_col[16];                 // NS=2: set-1 column j holds the partial sum that corrects set-0 column risky_col[j]
   int32_t lo_acc, hi_acc, lo_add, hi_add;
-  float mf, z_next, res_mf, z_res, s_out;
+  float mf, nbias;                       // M16 * 2^-n and -12582912 * mf
+  float z_next;
+  float res_mf, res_nbias, z_res;        // EPI_RESIDUAL: Mres * 2^-nres, -12582912 * res_mf, z_4
+  float s_out, out_off;                  // EPI_FINAL: f32(s_5), -(12582912 + z_5)
   int32_t relu, cout;
+  int32_t dbg;                           // SESRQ_UMMA_DBG bit mask (pipeline experiments only; results are wrong when set)
   // geometry
   int32_t B, H, W, TH, TW, tiles_x, tiles_y, num_tiles, pad;
   uint32_t box_bytes, stage_bytes, w_bytes;
   int32_t stages;                        // tile buffers in flight (2..MAX_STAGES)
-  int32_t pair_off[MAX_PAIRS];           // pixel offset of the first tap of the pair inside the tile
-  int32_t pair_lbo[MAX_PAIRS];           // pixel distance to the second tap
+  int32_t nbw;                           // issuer warps = row bands per tile (1..3)
   uint32_t idesc;
   // layer-0 kernel only
   int32_t cin;
@@ -158,33 +205,47 @@ struct UmmaParams {
 
 // ------------------------------------------------------------------------------------------------
 // epilogue of one output pixel: 16 (x NS) accumulator columns -> codes.  Shared by both kernels.
+// FLOOR: apply max(y, relu_floor) explicitly.  It is only needed for a ReLU layer whose consumer has z > -128:
+// with z <= -128, clamp(rint(max(y,0) + z)) == clamp(rint(y + z)) because every y < 0 saturates at -128 either way.
 // ------------------------------------------------------------------------------------------------
-template <int NS, int EPI, int RS>
-__device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, const int (&acc)[NS][16], const uint4 sc,
+template <int NS, int EPI, int RS, bool FLOOR>
+__device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[NS][16], const uint4 sc,
                                                uint4* __restrict__ out_px, int8_t* __restrict__ qb,
                                                float* __restrict__ yb, const long long HW, const float relu_floor) {
-  // ---- A = clampAdd(sum_p clampAcc(P_p)) + K  (quan_func.py:370,437,491) ----
-  int A[16];
+  // ---- m = bits of the float 12582912 + A,  A = clampAdd(sum_p clampAcc(P_p)) + K  (quan_func.py:370,437,491) ----
+  if (NS == 2) {
+    // the adder-tree clamp is proved inert for this layout; the few PE clamps that can fire are corrected here
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {              // NS = 2 carries at most 4 risky pairs (accumulator_sets)
+      if (j >= P.n_risky) break;
+      const int v = acc[1][j];
+      const int d = clampi(v, P.lo_acc, P.hi_acc) - v;
+      if (d != 0) {
+        const int col = P.risky_col[j];
+#pragma unroll
+        for (int n = 0; n < 16; ++n)
+          if (n == col) acc[0][n] += d;
+      }
+    }
+  }
+  float yv[16];
 #pragma unroll
   for (int n = 0; n < 16; ++n) {
-    if (NS == 1) {
-      A[n] = acc[0][n] + P.c_fused[n];
-    } else if (NS == 2) {
-      int s = acc[0][n] + P.c_sum[n];
-      if (P.xmask & (1u << n)) {
-        const int v = acc[NS - 1][n] + P.c_x[n];
-        s += clampi(v, P.lo_acc, P.hi_acc) - v;
-      }
-      A[n] = clampi(s, P.lo_add, P.hi_add) + P.c_k[n];
+    int m;
+    if (NS <= 2) {
+      m = acc[0][n];
     } else {
       int s = 0;
 #pragma unroll
-      for (int p = 0; p < NS; ++p) s += clampi(acc[p][n] + P.c_pe[p][n], P.lo_acc, P.hi_acc);
-      A[n] = clampi(s, P.lo_add, P.hi_add) + P.c_k[n];
+      for (int p = 0; p < NS; ++p) s += clampi(acc[p][n], P.lo_acc, P.hi_acc);
+      m = clampi(s, P.lo_add, P.hi_add) + P.c_kmagic[n];
     }
+    yv[n] = __fmaf_rn(__int_as_float(m), P.mf, P.nbias);                          // RN(A * M16 * 2^-n)  (:529)
+    if (FLOOR) yv[n] = fmaxf(yv[n], relu_floor);
   }
   if (EPI == EPI_FINAL) {
-    // q5 = clamp(rint(y + z5)); out = (q5 - z5) * s5 (:585,:594); columns are in natural channel order
+    // q5 = clamp(rint(y + z5)); out = (q5 - z5) * s5 (:585,:594); columns are in natural channel order.
+    // rint via the 1.5*2^23 trick: rm = 12582912 + q5 exactly, its low byte is the int8 code.
     constexpr int R2 = RS * RS;
     const long long HrWr = HW * R2;
     const int Wr = P.W * RS;
@@ -194,10 +255,11 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, const int (&
         float o[RS];
 #pragma unroll
         for (int j = 0; j < RS; ++j) {
-          const float yv = requant(A[n0 + j], P.mf);
-          const int q = min(max(__float2int_rn(__fadd_rn(yv, P.z_next)), -128), 127);
-          if (qb) qb[(long long)(n0 + j) * HW] = (int8_t)q;
-          o[j] = __fmul_rn(__fsub_rn((float)q, P.z_next), P.s_out);
+          float t = __fadd_rn(yv[n0 + j], P.z_next);
+          t = fminf(fmaxf(t, -128.f), 127.f);
+          const float rm = __fadd_rn(t, MAGIC_F);
+          if (qb) qb[(long long)(n0 + j) * HW] = (int8_t)__float_as_int(rm);
+          o[j] = __fmul_rn(__fadd_rn(rm, P.out_off), P.s_out);
         }
         if (yb) {
           float* dst = yb + (long long)(n0 / R2) * HrWr + (long long)((n0 % R2) / RS) * Wr;
@@ -207,44 +269,311 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, const int (&
         }
       }
     }
-  } else {
+  } else if (EPI == EPI_RESIDUAL) {
+    // ic = clamp(rint(relu(y) - 128)) (:251; the low clamp subsumes the ReLU), rc from the shortcut (:250),
+    // t = (rc + ic + 256) * Mres * 2^-nres (:252,:269), q4 = clamp(rint(t + z4)) (:270).
+    // Bytes: shortcut byte = rc + 128, (ic ^ 0x80) = ic + 128, so their sum IS rc + ic + 256.
     uint32_t ow[4];
     const uint32_t scw[4] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
+      int ic[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ic[j] = __float2int_rn(__fadd_rn(yv[4 * w + j], -128.f));
+      const uint32_t vic = pack4_sat_s8(ic[0], ic[1], ic[2], ic[3]) ^ 0x80808080u;
+      // 16-bit lanes: even bytes and odd bytes
+      const uint32_t s_even = (scw[w] & 0x00ff00ffu) + (vic & 0x00ff00ffu);
+      const uint32_t s_odd = __byte_perm(scw[w], 0u, 0x4341u) + __byte_perm(vic, 0u, 0x4341u);
       int q[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float a = fmaxf(requant(A[4 * w + j], P.mf), relu_floor);
-        if (EPI == EPI_RESIDUAL) {
-          const int ic = min(__float2int_rn(__fadd_rn(a, -128.f)), 127);         // :251 (a >= 0)
-          const int vrc = (int)__byte_perm(scw[w], 0u, 0x4440u + j);              // rc + 128 (:250)
-          const float tt = __fmul_rn((float)(vrc + ic + 128), P.res_mf);          // :252,:269
-          q[j] = __float2int_rn(__fadd_rn(tt, P.z_res));                          // :270, clamped by the pack
-        } else {
-          q[j] = __float2int_rn(__fadd_rn(a, P.z_next));                          // :280, clamped by the pack
-        }
+        const uint32_t lane16 = (j & 1) ? s_odd : s_even;
+        // bits of the float 12582912 + S: low two bytes from the 16-bit lane, high two from the magic constant
+        const uint32_t mb = __byte_perm(lane16, (uint32_t)MAGIC_BITS, (j & 2) ? 0x7632u : 0x7610u);
+        const float tt = __fmaf_rn(__uint_as_float(mb), P.res_mf, P.res_nbias);
+        q[j] = __float2int_rn(__fadd_rn(tt, P.z_res));
       }
-      ow[w] = pack4_sat_s8(q[0], q[1], q[2], q[3]) ^ 0x80808080u;                 // v = q + 128
+      ow[w] = pack4_sat_s8(q[0], q[1], q[2], q[3]) ^ 0x80808080u;
+    }
+    *out_px = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  } else {
+    uint32_t ow[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      int q[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q[j] = __float2int_rn(__fadd_rn(yv[4 * w + j], P.z_next));   // :280, clamped by the pack
+      ow[w] = pack4_sat_s8(q[0], q[1], q[2], q[3]) ^ 0x80808080u;                                // v = q + 128
     }
     *out_px = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
+// Epilogue warps, shared by both kernels.  A row slot cycles:  pre-loaded with c_init (tcgen05.st) + arrive on
+// acc_empty[slot]  ->  the issuer accumulates one 128-pixel output row on top  ->  tcgen05.ld, immediate re-load of
+// c_init, arrive.  Completion is signalled per group of RG consecutive rows of a tile (acc_full ring indexed by the
+// running group counter); warpgroup wg consumes the groups G == wg (mod NWG) and software-pipelines the TMEM loads
+// of a group's rows (row i+1 is in flight while row i is converted and stored).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void reg_fence16(int (&r)[16]) {
+  // the values were produced asynchronously (tcgen05.ld): pin every later use behind the preceding wait::ld
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+               "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+
+// TMEM <-> registers for one row slot.  NS = 2: only the first 4 columns of set 1 are live.
+template <int NS>
+__device__ __forceinline__ void slot_load(uint32_t taddr, int (&a)[NS][16]) {
+  tmem_ld16(taddr, a[0]);
+  if (NS == 2) tmem_ld4(taddr + 16, a[1]);
+  if (NS == 4) {
+#pragma unroll
+    for (int p = 1; p < NS; ++p) tmem_ld16(taddr + p * 16, a[p]);
+  }
+}
+template <int NS>
+__device__ __forceinline__ void slot_store(uint32_t taddr, const int (&a)[NS][16]) {
+  tmem_st16(taddr, a[0]);
+  if (NS == 2) tmem_st4(taddr + 16, a[1]);
+  if (NS == 4) {
+#pragma unroll
+    for (int p = 1; p < NS; ++p) tmem_st16(taddr + p * 16, a[p]);
+  }
+}
+template <int NS>
+__device__ __forceinline__ void slot_fence(int (&a)[NS][16]) {
+  reg_fence16(a[0]);
+  if (NS == 2) asm volatile("" : "+r"(a[1][0]), "+r"(a[1][1]), "+r"(a[1][2]), "+r"(a[1][3]));
+  if (NS == 4) {
+#pragma unroll
+    for (int p = 1; p < NS; ++p) reg_fence16(a[p]);
+  }
+}
+
+template <int NS, int EPI, int RS, bool FLOOR, int EPI_WARPS>
+__device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ewarp, const int lane, const uint32_t tmem_base,
+                                               uint64_t* acc_full, uint64_t* acc_empty,
+                                               const uint4* __restrict__ shortcut, uint4* __restrict__ out,
+                                               int8_t* __restrict__ q5, float* __restrict__ y) {
+  constexpr int NCOLS = 16 * NS;
+  constexpr int NSLOT = TMEM_COLS / NCOLS;
+  constexpr int NWG = EPI_WARPS / 4;
+  constexpr int RG = GroupRows<NS>::value;
+  static_assert(NSLOT % NWG == 0, "initial slot pre-load is dealt round-robin to the warpgroups");
+  const int wg = ewarp >> 2;                    // warpgroup
+  const int quarter = ewarp & 3;                // TMEM lane quarter this warp may access (== warp id % 4)
+  const int ox = quarter * 32 + lane;           // pitch == UMMA_M: a slot is one output row of the tile, lane is the column
+  const long long HW = (long long)P.H * P.W;
+  const float relu_floor = P.relu ? 0.f : -INFINITY;
+  const int tiles_per_frame = P.tiles_x * P.tiles_y;
+  const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+  int cinit[NS][16];
+#pragma unroll
+  for (int p = 0; p < NS; ++p)
+#pragma unroll
+    for (int n = 0; n < 16; ++n) cinit[p][n] = (NS == 2 && p == 1 && n >= 4) ? 0 : P.c_init[p][n];
+  for (int s = wg; s < NSLOT; s += NWG) slot_store<NS>(tq + s * NCOLS, cinit);
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0)
+    for (int s = wg; s < NSLOT; s += NWG) mbar_arrive(&acc_empty[s]);
+
+  constexpr int GPB = TB / RG;
+  const uint32_t nring = (uint32_t)ring_slots(NSLOT, P.TH);
+  RingPos ring;
+  uint32_t G0 = 0;                              // groups of all earlier tiles
+  for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ring.advance((uint32_t)P.TH, nring)) {
+    const int b = t / tiles_per_frame;
+    const int r = t - b * tiles_per_frame;
+    const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
+    const int y0 = ty * P.TH, gx = tx * P.TW + ox;
+    const int nblk = min(P.TH, P.H - y0);
+    const int ngrp = tile_groups<RG>(nblk);
+    const bool valid = (ox < P.TW) && (gx < P.W);
+    const long long pix0 = (long long)b * HW + (long long)y0 * P.W + gx;
+    const int first = (int)((wg + NWG - (G0 % NWG)) % NWG);
+    for (int j = first; j < ngrp; j += NWG) {
+      const uint32_t G = G0 + j;
+      const int mb0 = (j / GPB) * TB + (j % GPB) * RG;          // tile-local group j = band * GPB + group within the band
+      const int cnt = min(RG, nblk - mb0);
+      uint4 sc[RG];
+#pragma unroll
+      for (int i = 0; i < RG; ++i) {
+        sc[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (EPI == EPI_RESIDUAL && valid && i < cnt) sc[i] = __ldg(shortcut + pix0 + (long long)(mb0 + i) * P.W);
+      }
+      __syncwarp();                        // the .sync.aligned TMEM accesses below need a converged warp
+      mbar_wait(&acc_full[G % NSLOT], (G / NSLOT) & 1);
+      tc_fence_after();
+      int acc[2][NS][16];
+      uint32_t slot = ring.base + (uint32_t)mb0;
+      slot_load<NS>(tq + slot * NCOLS, acc[0]);
+#pragma unroll
+      for (int i = 0; i < RG; ++i) {
+        if (i < cnt) {                     // warp-uniform
+          const uint32_t taddr = tq + slot * NCOLS;
+          const uint32_t slot_cur = slot;
+          ++slot;
+          tmem_ld_wait();
+          slot_fence<NS>(acc[i & 1]);
+          if (i + 1 < RG && i + 1 < cnt) slot_load<NS>(tq + slot * NCOLS, acc[(i + 1) & 1]);   // next row in flight
+          if (!(P.dbg & 2)) {
+            slot_store<NS>(taddr, cinit);
+            tmem_st_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[slot_cur]);
+
+          if (valid && !(P.dbg & 1)) {
+            const int mb = mb0 + i;
+            const long long pix = pix0 + (long long)mb * P.W;
+            float* yb = nullptr;
+            int8_t* qb = nullptr;
+            if (EPI == EPI_FINAL) {
+              constexpr int R2 = RS * RS;
+              if (y) yb = y + (long long)b * (P.cout / R2) * (HW * R2) + (long long)(y0 + mb) * RS * (P.W * RS) + (long long)gx * RS;
+              if (q5) qb = q5 + (long long)b * P.cout * HW + (long long)(y0 + mb) * P.W + gx;
+            }
+            epilogue_pixel<NS, EPI, RS, FLOOR>(P, acc[i & 1], sc[i], out + pix, qb, yb, HW, relu_floor);
+          }
+        }
+      }
+    }
+    G0 += ngrp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MMA issuer (one thread per CTA), shared by both kernels.
+//
+// An M128 x K32 tcgen05.mma streams 4 KB of A operand from shared memory whatever N is (measured: ~30 cycles
+// per instruction at N = 16, profiles/r1 pipeline experiments), so the cost of a layer is the number of MMAs.
+// The vertical taps are therefore batched into N: input row r of the tile contributes to the KS output rows
+// o = r - dy, whose accumulators are KS CONSECUTIVE TMEM slots, so one MMA with N = KS * NCOLS per
+// (input row, horizontal tap pair) updates all of them at once:
+//     D[slot(o)][pixel X][co] += sum_{dx in pair, c} in[r][X + dx][c] * W[dy = r - o][dx][co]
+// The B image holds, per tap pair and K half, the row blocks in order dy = KS-1 .. 0 so that ascending output
+// rows see ascending D columns; tile edges simply use a sub-range of blocks (smaller N, offset B start).
+// 3x3: 2 MMAs per row instead of 5; 5x5: 3 instead of 13; layer 0 (K = all 8 dx of one row): 1 instead of 5.
+// Horizontal shifts stay in the A descriptor (start address = pixel offset, LBO = distance to the second tap).
+// ------------------------------------------------------------------------------------------------
+// What limits this kernel is the instruction stream of the issuing THREAD, not the tensor pipe (tools/mma_probe*.cu
+// on B200: an M128 x K32 kind::i8 MMA occupies the pipe for ~32 + N/4 cycles -- both operands stream from shared
+// memory at 128 B/clk -- for any accumulator address pattern, but a lone thread issues at most one MMA per ~51
+// cycles, pays ~5 cycles per additional dependent instruction, ~185 per tcgen05.commit and ~200 per
+// mbarrier.try_wait + tcgen05.fence).  Hence:
+//   * a tile's output rows are split into `nbw` bands of TB rows, each issued by its own warp (warps 1..nbw).  A
+//     band's MMAs touch only that band's accumulator slots (edge rows use a sub-range of the B row blocks), so the
+//     warps are independent: no ordering between them, each tracks its own completions;
+//   * slot readiness (acc_empty, one barrier per row slot) is polled once per band by TB lanes at once;
+//   * completion is signalled per GROUP of RG consecutive rows (one tcgen05.commit per group; barrier ring acc_full
+//     indexed by a running group counter); an epilogue warpgroup consumes one group at a time;
+//   * the code for a full band is completely unrolled: every operand is `band base + compile-time offset`.
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+
+// MMAs of input row r (band-relative, 0 .. rows + KS - 2) of a band with `rows` output rows.
+//   output rows o = r - dy, clipped to [0, rows); B row block jblk = o - (r - KS + 1)  <->  dy = KS - 1 - jblk.
+template <int KS, int NS, int NPAIR, int ROW_UNITS, int PAIR_STEP>
+__device__ __forceinline__ void issue_row(const int r, const int rows, const uint32_t d_band, const uint32_t a_band_lo,
+                                          const uint32_t w_units, const uint32_t idesc0) {
+  constexpr int NCOLS = 16 * NS;
+  constexpr int NTOT = KS * NCOLS;                           // rows of the B image per K half
+  constexpr int JMAX = (256 / NCOLS) < KS ? (256 / NCOLS) : KS;   // row blocks per instruction (N <= 256)
+  // cute::UMMA::SmemDescriptor high word: SBO = 128 B (bits 32-45), version 1 (bit 46), no swizzle
+  const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t b_lbo = (uint32_t)NTOT << 16;
+  const int o_first = r - (KS - 1);
+  const int o_lo = o_first < 0 ? 0 : o_first;
+  const int o_hi = r < rows - 1 ? r : rows - 1;
+#pragma unroll
+  for (int o = o_lo; o <= o_hi; o += JMAX) {
+    const int cnt = (o_hi - o + 1) < JMAX ? (o_hi - o + 1) : JMAX;
+    const int jblk = o - o_first;
+    const uint32_t idesc = idesc0 | ((uint32_t)((cnt * NCOLS) >> 3) << 17);
+#pragma unroll
+    for (int q = 0; q < NPAIR; ++q)
+      umma_i8(d_band + (uint32_t)(o * NCOLS), make_desc(a_band_lo + (uint32_t)(r * ROW_UNITS + q * PAIR_STEP), desc_hi),
+              make_desc((w_units + (uint32_t)(q * 2 * NTOT + jblk * NCOLS)) | b_lbo, desc_hi), idesc, 1u);
+  }
+}
+
+// One band of one tile.  Called by the whole issuer warp (converged); lane 0 issues the tcgen05 instructions.
+// nblk: rows of the tile that exist; ring: slot base / parity of the tile; Gt: groups of all earlier tiles.
+template <int KS, int NS, int NPAIR, int ROW_UNITS, int PAIR_STEP>
+__device__ __forceinline__ void mma_issue_band(const int bw, const int lane, const uint32_t tmem_base, const uint32_t a_tile,
+                                               const uint32_t a_lbo, const uint32_t w_units, const uint32_t idesc0,
+                                               const int nblk, const RingPos ring, const uint32_t Gt,
+                                               const uint32_t acc_full_addr, const uint32_t acc_empty_addr) {
+  constexpr int NCOLS = 16 * NS;
+  constexpr int NSLOT = TMEM_COLS / NCOLS;
+  constexpr int RG = GroupRows<NS>::value;
+  constexpr int GPB = TB / RG;
+  const int rows = min(TB, nblk - bw * TB);                  // output rows of this band that exist (may be <= 0)
+  const uint32_t slot0 = ring.base + (uint32_t)(bw * TB);
+  // ---- all TB slots of the band pre-loaded?  (lane l <-> band row l) ----
+  {
+    const uint32_t bar = acc_empty_addr + (slot0 + (uint32_t)(lane & (TB - 1))) * 8u;
+    while (!__all_sync(0xffffffffu, mbar_test(bar, ring.par) != 0u)) {}
+    tc_fence_after();
+    // rows the tile does not have: nobody will consume their slot, so complete its phase here (4 = arrivals of a
+    // consuming warpgroup); the slot stays pre-loaded
+    if (lane < TB && lane >= max(rows, 0))
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], 4;" ::"r"(bar) : "memory");
+  }
+  if (rows > 0 && elect_one()) {          // elect.sync: the compiler keeps the block on the uniform datapath
+    const uint32_t d_band = tmem_base + slot0 * NCOLS;
+    const uint32_t a_band_lo = (a_tile + (uint32_t)(bw * TB * ROW_UNITS)) | (a_lbo << 16);
+    const uint32_t Gb = Gt + (uint32_t)(bw * GPB);
+    if (rows == TB) {
+#pragma unroll
+      for (int r = 0; r < TB + KS - 1; ++r) {
+        issue_row<KS, NS, NPAIR, ROW_UNITS, PAIR_STEP>(r, TB, d_band, a_band_lo, w_units, idesc0);
+        const int o_done = r - (KS - 1);
+        if (o_done >= 0 && (o_done % RG) == RG - 1) umma_commit_addr(acc_full_addr + ((Gb + (uint32_t)(o_done / RG)) % NSLOT) * 8u);
+      }
+    } else {
+      for (int r = 0; r < rows + KS - 1; ++r) {
+        issue_row<KS, NS, NPAIR, ROW_UNITS, PAIR_STEP>(r, rows, d_band, a_band_lo, w_units, idesc0);
+        const int o_done = r - (KS - 1);
+        if (o_done >= 0 && ((o_done % RG) == RG - 1 || o_done == rows - 1))
+          umma_commit_addr(acc_full_addr + ((Gb + (uint32_t)(o_done / RG)) % NSLOT) * 8u);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
 // the kernel.  KS: kernel size; NS: accumulator sets (1/2/4, see header); EPI: EpilogueKind; RS: PixelShuffle
 // factor of the final epilogue (1 otherwise); EPI_WARPS: number of epilogue warps.
 // ------------------------------------------------------------------------------------------------
-template <int KS, int NS, int EPI, int RS, int EPI_WARPS>
+template <int KS, int NS, int EPI, int RS, bool FLOOR, int EPI_WARPS>
 __global__ void __launch_bounds__((CTRL_WARPS + EPI_WARPS) * 32, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ UmmaParams P,
                  const uint8_t* __restrict__ w_img, const uint4* __restrict__ shortcut, uint4* __restrict__ out,
                  int8_t* __restrict__ q5, float* __restrict__ y) {
   constexpr int NCOLS = 16 * NS;
   constexpr int NSLOT = TMEM_COLS / NCOLS;
-  constexpr int NP = (KS * KS + 1) / 2;   // tap pairs = MMAs per accumulator block
-  constexpr int NWG = EPI_WARPS / 4;
-  static_assert(NSLOT % NWG == 0, "slot ownership must be stable per warpgroup");
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* const tile0 = smem;
@@ -267,7 +596,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
     for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(&tile_full[i], 1);
-      mbar_init(&tile_empty[i], MMA_WARPS);
+      mbar_init(&tile_empty[i], P.nbw);
     }
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&acc_full[s], 1);
@@ -299,101 +628,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       }
     }
   } else if (warp < CTRL_WARPS) {
-    // ================= MMA issuers (warps 1..3) =================
-    const int mw = warp - 1;
-    const bool leader = elect_one();
-    uint32_t a_lo[NP], b_lo[NP];
-    const uint32_t w_addr = smem_u32(w_s);
-#pragma unroll
-    for (int pr = 0; pr < NP; ++pr) {
-      a_lo[pr] = (uint32_t)P.pair_off[pr] | ((uint32_t)P.pair_lbo[pr] << 16);                 // 16-byte units
-      b_lo[pr] = (((w_addr + (uint32_t)pr * (2u * NCOLS * 16u)) & 0x3FFFFu) >> 4) | ((uint32_t)NCOLS << 16);
-    }
-    // cute::UMMA::SmemDescriptor high word: SBO = 128 B (bits 32-45), version 1 (bit 46), no swizzle
-    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-    const uint32_t idesc = P.idesc;
-    const uint32_t tile_addr0 = (smem_u32(tile0) & 0x3FFFFu) >> 4;
-    int st = 0;
-    uint32_t ph = 0;
-    uint32_t g0 = 0;
-    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
-      const int r = t % tiles_per_frame;
-      const int nblk = min(P.TH, P.H - (r / P.tiles_x) * P.TH);     // rows of this tile that exist
-      mbar_wait(&tile_full[st], ph);
-      tc_fence_after();
-      const uint32_t a_base = tile_addr0 + (uint32_t)st * (P.stage_bytes >> 4);
-      for (int mb = mw; mb < nblk; mb += MMA_WARPS) {
-        const uint32_t g = g0 + mb;
-        const uint32_t slot = g % NSLOT;
-        mbar_wait(&acc_empty[slot], ((g / NSLOT) & 1) ^ 1);
+    // ================= MMA issuer warps 1 .. nbw (one band of every tile each) =================
+    const int bw = warp - 1;
+    if (bw < P.nbw) {
+      constexpr int NPAIR = (KS + 1) / 2;
+      constexpr int RG = GroupRows<NS>::value;
+      const uint32_t w_units = (smem_u32(w_s) & 0x3FFFFu) >> 4;
+      const uint32_t tile_addr0 = (smem_u32(tile0) & 0x3FFFFu) >> 4;
+      const uint32_t nring = (uint32_t)ring_slots(NSLOT, P.TH);
+      int st = 0;
+      uint32_t ph = 0;
+      uint32_t Gt = 0;
+      RingPos ring;
+      for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+        const int r = t % tiles_per_frame;
+        const int nblk = min(P.TH, P.H - (r / P.tiles_x) * P.TH);     // rows of this tile that exist
+        mbar_wait(&tile_full[st], ph);
         tc_fence_after();
-        if (leader) {
-          const uint32_t d = tmem_base + slot * NCOLS;
-          const uint32_t row = a_base + (uint32_t)mb * (UMMA_M * 16 / 16);
-#pragma unroll
-          for (int pr = 0; pr < NP; ++pr) {
-            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo[pr] + row);
-            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)b_lo[pr];
-            umma_i8(d, ad, bd, idesc, pr > 0 ? 1u : 0u);
-          }
-          umma_commit(&acc_full[slot]);       // implies tcgen05.fence::before_thread_sync
-        }
+        // A: row pitch 128 pixels; pair q = taps (2q, 2q+1) of the row: start 2q pixels in, LBO = one pixel
+        mma_issue_band<KS, NS, NPAIR, UMMA_M, 2>(bw, lane, tmem_base, tile_addr0 + (uint32_t)st * (P.stage_bytes >> 4), 1u,
+                                                 w_units, P.idesc, nblk, ring, Gt, smem_u32(acc_full), smem_u32(acc_empty));
+        if (lane == 0) umma_commit(&tile_empty[st]);     // fires when this warp's MMAs on the tile have retired
         __syncwarp();
+        Gt += tile_groups<RG>(nblk);
+        ring.advance((uint32_t)P.TH, nring);
+        if (++st == P.stages) { st = 0; ph ^= 1; }
       }
-      if (leader) umma_commit(&tile_empty[st]);   // fires when this warp's MMAs on the tile have retired
-      __syncwarp();
-      g0 += nblk;
-      if (++st == P.stages) { st = 0; ph ^= 1; }
     }
   } else {
     // ================= epilogue =================
-    const int wg = (warp - CTRL_WARPS) >> 2;      // warpgroup
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int ox = quarter * 32 + lane;           // pitch == UMMA_M: block b is output row b, lane is the column
-    const long long HW = (long long)P.H * P.W;
-    const float relu_floor = P.relu ? 0.f : -INFINITY;
-    uint32_t g0 = 0;
-    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
-      const int b = t / tiles_per_frame;
-      const int r = t - b * tiles_per_frame;
-      const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
-      const int y0 = ty * P.TH, gx = tx * P.TW + ox;
-      const int nblk = min(P.TH, P.H - y0);
-      const bool valid = (ox < P.TW) && (gx < P.W);
-      const long long pix0 = (long long)b * HW + (long long)y0 * P.W + gx;
-      const int first = (int)((wg + NWG - (g0 % NWG)) % NWG);
-      for (int mb = first; mb < nblk; mb += NWG) {
-        const uint32_t g = g0 + mb;
-        const uint32_t slot = g % NSLOT;
-        const long long pix = pix0 + (long long)mb * P.W;
-        uint4 sc = make_uint4(0u, 0u, 0u, 0u);
-        if (EPI == EPI_RESIDUAL && valid) sc = __ldg(shortcut + pix);
-
-        __syncwarp();                        // the .sync.aligned TMEM loads below need a converged warp
-        mbar_wait(&acc_full[slot], (g / NSLOT) & 1);
-        tc_fence_after();
-        int acc[NS][16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * NCOLS;
-#pragma unroll
-        for (int p = 0; p < NS; ++p) tmem_ld16(taddr + p * 16, acc[p]);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[slot]);
-
-        if (valid) {
-          float* yb = nullptr;
-          int8_t* qb = nullptr;
-          if (EPI == EPI_FINAL) {
-            constexpr int R2 = RS * RS;
-            if (y) yb = y + (long long)b * (P.cout / R2) * (HW * R2) + (long long)(y0 + mb) * RS * (P.W * RS) + (long long)gx * RS;
-            if (q5) qb = q5 + (long long)b * P.cout * HW + (long long)(y0 + mb) * P.W + gx;
-          }
-          epilogue_pixel<NS, EPI, RS>(P, acc, sc, out + pix, qb, yb, HW, relu_floor);
-        }
-      }
-      g0 += nblk;
-    }
+    epilogue_warps<NS, EPI, RS, FLOOR, EPI_WARPS>(P, warp - CTRL_WARPS, lane, tmem_base, acc_full, acc_empty, shortcut, out, q5, y);
   }
 
   // ---- teardown ----
@@ -440,15 +704,13 @@ struct ExactDiv {
   }
 };
 
-template <int KS, int NS, int CIN, int EPI_WARPS>
+template <int KS, int NS, int CIN, bool FLOOR, int EPI_WARPS>
 __global__ void __launch_bounds__((CTRL_WARPS + EPI_WARPS + L0_BUILD_WARPS) * 32, 1)
 conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restrict__ w_img,
                     const float* __restrict__ x, uint4* __restrict__ out) {
   constexpr int NCOLS = 16 * NS;
   constexpr int NSLOT = TMEM_COLS / NCOLS;
-  constexpr int NWG = EPI_WARPS / 4;
   constexpr int PAD = (KS - 1) / 2;
-  static_assert(NSLOT % NWG == 0, "slot ownership must be stable per warpgroup");
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* const e0 = smem;                                         // E planes: P.stages buffers of stage_bytes
@@ -471,7 +733,7 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(&e_full[i], L0_BUILD_WARPS);
-      mbar_init(&e_empty[i], MMA_WARPS);
+      mbar_init(&e_empty[i], P.nbw);
     }
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&acc_full[s], 1);
@@ -490,83 +752,36 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
   if (warp == 0) {
     // idle (no TMA in this kernel: the operand plane is computed, not copied)
   } else if (warp < CTRL_WARPS) {
-    // ================= MMA issuers =================
-    const int mw = warp - 1;
-    const bool leader = elect_one();
-    uint32_t b_lo[KS];
-    const uint32_t w_addr = smem_u32(w_s);
-#pragma unroll
-    for (int dy = 0; dy < KS; ++dy)
-      b_lo[dy] = (((w_addr + (uint32_t)dy * (2u * NCOLS * 16u)) & 0x3FFFFu) >> 4) | ((uint32_t)NCOLS << 16);
-    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-    const uint32_t idesc = P.idesc;
-    const uint32_t e_addr0 = (smem_u32(e0) & 0x3FFFFu) >> 4;
-    int st = 0;
-    uint32_t ph = 0;
-    uint32_t g0 = 0;
-    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
-      const int r = t % tiles_per_frame;
-      const int nblk = min(P.TH, P.H - (r / P.tiles_x) * P.TH);
-      mbar_wait(&e_full[st], ph);
-      tc_fence_after();
-      const uint32_t a_base = e_addr0 + (uint32_t)st * (P.stage_bytes >> 4);
-      for (int mb = mw; mb < nblk; mb += MMA_WARPS) {
-        const uint32_t g = g0 + mb;
-        const uint32_t slot = g % NSLOT;
-        mbar_wait(&acc_empty[slot], ((g / NSLOT) & 1) ^ 1);
+    // ================= MMA issuer warps 1 .. nbw =================
+    const int bw = warp - 1;
+    if (bw < P.nbw) {
+      constexpr int RG = GroupRows<NS>::value;
+      const uint32_t w_units = (smem_u32(w_s) & 0x3FFFFu) >> 4;
+      const uint32_t e_addr0 = (smem_u32(e0) & 0x3FFFFu) >> 4;
+      const uint32_t nring = (uint32_t)ring_slots(NSLOT, P.TH);
+      int st = 0;
+      uint32_t ph = 0;
+      uint32_t Gt = 0;
+      RingPos ring;
+      for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+        const int r = t % tiles_per_frame;
+        const int nblk = min(P.TH, P.H - (r / P.tiles_x) * P.TH);
+        mbar_wait(&e_full[st], ph);
         tc_fence_after();
-        if (leader) {
-          const uint32_t d = tmem_base + slot * NCOLS;
-#pragma unroll
-          for (int dy = 0; dy < KS; ++dy) {
-            const uint32_t a_lo = (a_base + (uint32_t)(mb + dy) * L0_EP) | (4u << 16);     // LBO = 4 entries = 64 B
-            umma_i8(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo[dy], idesc, dy > 0 ? 1u : 0u);
-          }
-          umma_commit(&acc_full[slot]);
-        }
+        // A: E plane, row pitch L0_EP entries; one K = 32 chunk covers taps dx = 0..7 of a row: LBO = 4 entries
+        mma_issue_band<KS, NS, 1, L0_EP, 0>(bw, lane, tmem_base, e_addr0 + (uint32_t)st * (P.stage_bytes >> 4), 4u, w_units,
+                                            P.idesc, nblk, ring, Gt, smem_u32(acc_full), smem_u32(acc_empty));
+        if (lane == 0) umma_commit(&e_empty[st]);
         __syncwarp();
+        Gt += tile_groups<RG>(nblk);
+        ring.advance((uint32_t)P.TH, nring);
+        if (++st == P.stages) { st = 0; ph ^= 1; }
       }
-      if (leader) umma_commit(&e_empty[st]);
-      __syncwarp();
-      g0 += nblk;
-      if (++st == P.stages) { st = 0; ph ^= 1; }
     }
   } else if (warp < CTRL_WARPS + EPI_WARPS) {
-    // ================= epilogue (identical to the 16-channel kernel, EPI_PLAIN) =================
-    const int wg = (warp - CTRL_WARPS) >> 2;
-    const int quarter = warp & 3;
-    const int ox = quarter * 32 + lane;
-    const float relu_floor = P.relu ? 0.f : -INFINITY;
-    uint32_t g0 = 0;
-    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
-      const int b = t / tiles_per_frame;
-      const int r = t - b * tiles_per_frame;
-      const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
-      const int y0 = ty * P.TH, gx = tx * P.TW + ox;
-      const int nblk = min(P.TH, P.H - y0);
-      const bool valid = (ox < P.TW) && (gx < P.W);
-      const long long pix0 = (long long)b * HW + (long long)y0 * P.W + gx;
-      const int first = (int)((wg + NWG - (g0 % NWG)) % NWG);
-      for (int mb = first; mb < nblk; mb += NWG) {
-        const uint32_t g = g0 + mb;
-        const uint32_t slot = g % NSLOT;
-        __syncwarp();
-        mbar_wait(&acc_full[slot], (g / NSLOT) & 1);
-        tc_fence_after();
-        int acc[NS][16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * NCOLS;
-#pragma unroll
-        for (int p = 0; p < NS; ++p) tmem_ld16(taddr + p * 16, acc[p]);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[slot]);
-        if (valid)
-          epilogue_pixel<NS, EPI_PLAIN, 1>(P, acc, make_uint4(0u, 0u, 0u, 0u), out + pix0 + (long long)mb * P.W, nullptr,
-                                           nullptr, HW, relu_floor);
-      }
-      g0 += nblk;
-    }
+    // ================= epilogue (shared with the 16-channel kernel, EPI_PLAIN) =================
+    epilogue_warps<NS, EPI_PLAIN, 1, FLOOR, EPI_WARPS>(P, warp - CTRL_WARPS, lane, tmem_base, acc_full, acc_empty, nullptr, out,
+                                                       nullptr, nullptr);
   } else {
     // ================= builders =================
     const int bt = threadIdx.x - (CTRL_WARPS + EPI_WARPS) * 32;       // 0 .. 255
@@ -660,10 +875,17 @@ static EncodeTiledFn get_encode_fn() {
 
 static bool is_l0_layout(const LayerConst& c) { return c.cin <= 4; }
 
+// explicit max(y, 0) is only needed for a ReLU layer whose consumer's zero point is above -128 (see epilogue_pixel)
+static bool needs_floor(const LayerConst& c) { return c.epi == EPI_PLAIN && c.relu && c.z_next > -128.f; }
+
 bool umma_supported(const LayerConst& c) {
   // layer 0: fp32 frames with cin <= 4 (any input zero point: the builder writes the pad value itself);
   // other layers: 16 input channels from an NHWC16 tensor whose out-of-frame value is byte 0 (z' == -128).
   // Anything else runs on the generic path.
+  // The float-bits accumulator (MAGIC_BITS + A) needs |A| < 2^22: A is bounded by the adder clamp plus the
+  // 16-bit constant, so pe_add_bits <= 22 suffices.  The final epilogue needs 12582912 + z5 exact in fp32.
+  if (c.hi_add >= (1 << 21) || c.hi_acc >= (1 << 21)) return false;
+  if (c.epi == EPI_FINAL && (c.relu || !(fabsf(c.z_next) <= 1048576.f))) return false;
   if (is_l0_layout(c)) return c.epi == EPI_PLAIN && c.save_rc == 0 && (c.k == 3 || c.k == 5);
   if (!(c.cin == 16 && c.pad_byte == 0 && c.save_rc == 0 && (c.k == 3 || c.k == 5))) return false;
   if (c.epi == EPI_FINAL && !(c.r_shuffle == 1 || c.r_shuffle == 2 || c.r_shuffle == 4)) return false;
@@ -673,34 +895,72 @@ bool umma_supported(const LayerConst& c) {
 // Accumulator layout for this layer (see header): 1, 2 or 4 sets of 16 columns.
 static int accumulator_sets(const LayerConst& c) {
   if (!c.pe_exact) return 1;
-  for (int co = 0; co < c.cout; ++co)
+  if (!c.add_inert) return 4;                  // the adder-tree clamp can fire: literal tree
+  int pairs = 0;
+  for (int co = 0; co < c.cout; ++co) {
     if (c.pe_risky[co] > 3) return 4;          // more than one PE of a channel can clamp
-  return 2;
+    if (c.pe_risky[co] >= 0) ++pairs;
+  }
+  return pairs <= 4 ? 2 : 4;                   // NS = 2 keeps 4 correction columns live
 }
 
-// B operand image: for every tap pair, [2 K-halves][N/8 row groups][8 rows][16 B]; row n of set s holds the
-// weights of output channel col_chan(n) for the 16 input-channel bytes, masked per set as the layout requires.
-// Layer-0 image: one K=32 chunk per tap row dy; byte k of half h <-> tap dx = 4h + k/4, input channel k%4
-// (PE p == channel p for cin <= 4).
+// NS = 2: the (channel, PE) pairs whose 18-bit clamp can fire, in set-0 column order.  Set-1 column j carries the
+// partial sum of pair j; cols[j] is the set-0 column it corrects, chans[j] / pes[j] the channel and PE.
+static int risky_pairs(const LayerConst& c, bool natural, int* cols, int* chans, int* pes) {
+  int cnt = 0;
+  for (int n = 0; n < 16; ++n) {
+    const int co = natural ? n : chan_of_byte(n);
+    if (co >= c.cout || c.pe_risky[co] < 0) continue;
+    cols[cnt] = n; chans[cnt] = co; pes[cnt] = c.pe_risky[co];
+    ++cnt;
+  }
+  return cnt;
+}
+
+// (output channel, PE mask) of accumulator column n (set = n / 16) for layout ns; co < 0: zero row
+static void column_role(const LayerConst& c, int ns, bool natural, int n, int* co_out, int* only_pe) {
+  const int set = n / 16, nn = n % 16;
+  *only_pe = -1;
+  *co_out = -1;
+  if (ns == 2 && set == 1) {
+    int cols[16], chans[16], pes[16];
+    const int cnt = risky_pairs(c, natural, cols, chans, pes);
+    if (nn < cnt) { *co_out = chans[nn]; *only_pe = pes[nn]; }
+    return;
+  }
+  const int co = natural ? nn : chan_of_byte(nn);
+  if (co >= c.cout) return;
+  *co_out = co;
+  if (ns == 4) *only_pe = set;
+}
+
+// B operand image (see mma_issue_tile): [tap pair q][K half h][row block jblk <-> dy = k-1-jblk][N columns][16 B].
+// Row (jblk, n) of pair q, half h holds the weights of tap (dy, dx = 2q + h) for the output channel / PE mask that
+// accumulator column n stands for, over the 16 input-channel bytes (zero rows for dx >= k).
+// Layer-0 image: one pair; byte k of half h <-> tap dx = 4h + k/4, input channel k%4 (PE p == channel p for cin <= 4).
+static int umma_upload(LayerDev& L, const std::vector<uint8_t>& img, const char* what) {
+  if (cudaMalloc(&L.d_wumma, img.size()) != cudaSuccess ||
+      cudaMemcpy(L.d_wumma, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_cuda_error(cudaGetLastError(), what);
+    return SESRQ_ECUDA;
+  }
+  return SESRQ_OK;
+}
+
 static int umma_prepare_layer0(LayerDev& L, const int8_t* w) {
   const LayerConst& c = L.c;
   const int ns = accumulator_sets(c);
-  const int N = 16 * ns;
+  const int N = 16 * ns, NTOT = c.k * N;
   L.umma_n = N;
-  std::vector<uint8_t> img((size_t)c.k * 2 * N * 16, 0);
-  for (int dy = 0; dy < c.k; ++dy)
-    for (int h = 0; h < 2; ++h)
+  std::vector<uint8_t> img((size_t)2 * NTOT * 16, 0);
+  for (int h = 0; h < 2; ++h)
+    for (int jblk = 0; jblk < c.k; ++jblk) {
+      const int dy = c.k - 1 - jblk;
       for (int n = 0; n < N; ++n) {
-        const int set = n / 16, nn = n % 16;
-        const int co = chan_of_byte(nn);
-        if (co >= c.cout) continue;
-        int only_pe = -1;
-        if (ns == 4) only_pe = set;
-        if (ns == 2 && set == 1) {
-          if (c.pe_risky[co] < 0) continue;
-          only_pe = c.pe_risky[co];
-        }
-        uint8_t* row = img.data() + (((size_t)dy * 2 + h) * N + n) * 16;
+        int co, only_pe;
+        column_role(c, ns, false, n, &co, &only_pe);
+        if (co < 0) continue;
+        uint8_t* row = img.data() + (((size_t)h * NTOT) + (size_t)jblk * N + n) * 16;
         for (int k = 0; k < 16; ++k) {
           const int dx = 4 * h + k / 4, ci = k % 4;
           if (dx >= c.k || ci >= c.cin) continue;
@@ -708,58 +968,46 @@ static int umma_prepare_layer0(LayerDev& L, const int8_t* w) {
           row[k] = (uint8_t)w[(((size_t)co * c.cin + ci) * c.k + dy) * c.k + dx];
         }
       }
-  if (cudaMalloc(&L.d_wumma, img.size()) != cudaSuccess ||
-      cudaMemcpy(L.d_wumma, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
-    set_cuda_error(cudaGetLastError(), "umma layer-0 weight upload");
-    return SESRQ_ECUDA;
-  }
-  return SESRQ_OK;
+    }
+  return umma_upload(L, img, "umma layer-0 weight upload");
 }
 
 int umma_prepare_layer(LayerDev& L, const int8_t* w) {
   const LayerConst& c = L.c;
   if (is_l0_layout(c)) return umma_prepare_layer0(L, w);
-  const int taps = c.k * c.k, pairs = (taps + 1) / 2;
+  const int taps = c.k * c.k, pairs = (c.k + 1) / 2;
   const int ns = accumulator_sets(c);
-  const int N = 16 * ns;
+  const int N = 16 * ns, NTOT = c.k * N;
   L.umma_n = N;
-  std::vector<uint8_t> img((size_t)pairs * 2 * N * 16, 0);
+  std::vector<uint8_t> img((size_t)pairs * 2 * NTOT * 16, 0);
   const bool natural = (c.epi == EPI_FINAL);
-  for (int pr = 0; pr < pairs; ++pr)
+  for (int q = 0; q < pairs; ++q)
     for (int h = 0; h < 2; ++h) {
-      const int t = 2 * pr + h;
-      if (t >= taps) continue;
-      for (int n = 0; n < N; ++n) {
-        const int set = n / 16, nn = n % 16;
-        const int co = natural ? nn : chan_of_byte(nn);
-        if (co >= c.cout) continue;
-        int only_pe = -1;                      // -1: all PEs
-        if (ns == 4) only_pe = set;
-        if (ns == 2 && set == 1) {
-          if (c.pe_risky[co] < 0) continue;    // no risky PE: zero rows
-          only_pe = c.pe_risky[co];
-        }
-        uint8_t* row = img.data() + (((size_t)pr * 2 + h) * N + n) * 16;
-        for (int j = 0; j < 16; ++j) {
-          const int ci = chan_of_byte(j);
-          if (ci >= c.cin) continue;
-          if (only_pe >= 0 && (j >> 2) != only_pe) continue;
-          row[j] = (uint8_t)w[((size_t)co * c.cin + ci) * taps + t];
+      const int dx = 2 * q + h;
+      if (dx >= c.k) continue;
+      for (int jblk = 0; jblk < c.k; ++jblk) {
+        const int dy = c.k - 1 - jblk;
+        for (int n = 0; n < N; ++n) {
+          int co, only_pe;
+          column_role(c, ns, natural, n, &co, &only_pe);
+          if (co < 0) continue;
+          uint8_t* row = img.data() + ((((size_t)q * 2 + h) * NTOT) + (size_t)jblk * N + n) * 16;
+          for (int j = 0; j < 16; ++j) {
+            const int ci = chan_of_byte(j);
+            if (ci >= c.cin) continue;
+            if (only_pe >= 0 && (j >> 2) != only_pe) continue;
+            row[j] = (uint8_t)w[((size_t)co * c.cin + ci) * taps + dy * c.k + dx];
+          }
         }
       }
     }
-  if (cudaMalloc(&L.d_wumma, img.size()) != cudaSuccess ||
-      cudaMemcpy(L.d_wumma, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
-    set_cuda_error(cudaGetLastError(), "umma weight upload");
-    return SESRQ_ECUDA;
-  }
-  return SESRQ_OK;
+  return umma_upload(L, img, "umma weight upload");
 }
 
-template <int KS, int NS, int EPI, int RS, int EPI_WARPS>
+template <int KS, int NS, int EPI, int RS, bool FLOOR, int EPI_WARPS>
 static int launch_one(const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L, const uint8_t* d_shortcut,
                       uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem, cudaStream_t st) {
-  auto kern = conv_umma_kernel<KS, NS, EPI, RS, EPI_WARPS>;
+  auto kern = conv_umma_kernel<KS, NS, EPI, RS, FLOOR, EPI_WARPS>;
   static bool attr_set = false;
   if (!attr_set) {
     SESRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -775,11 +1023,17 @@ template <int KS, int NS, int EPI_WARPS>
 static int launch_epi(const LayerConst& c, const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L,
                       const uint8_t* d_shortcut, uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem,
                       cudaStream_t st) {
-  if (c.epi == EPI_PLAIN) return launch_one<KS, NS, EPI_PLAIN, 1, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
-  if (c.epi == EPI_RESIDUAL) return launch_one<KS, NS, EPI_RESIDUAL, 1, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
-  if (c.r_shuffle == 4) return launch_one<KS, NS, EPI_FINAL, 4, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
-  if (c.r_shuffle == 2) return launch_one<KS, NS, EPI_FINAL, 2, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
-  return launch_one<KS, NS, EPI_FINAL, 1, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+#define SESRQ_GO(EPI_, RS_, FLOOR_) \
+  return launch_one<KS, NS, EPI_, RS_, FLOOR_, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st)
+  if (c.epi == EPI_PLAIN) {
+    if (needs_floor(c)) SESRQ_GO(EPI_PLAIN, 1, true);
+    SESRQ_GO(EPI_PLAIN, 1, false);
+  }
+  if (c.epi == EPI_RESIDUAL) SESRQ_GO(EPI_RESIDUAL, 1, false);
+  if (c.r_shuffle == 4) SESRQ_GO(EPI_FINAL, 4, false);
+  if (c.r_shuffle == 2) SESRQ_GO(EPI_FINAL, 2, false);
+  SESRQ_GO(EPI_FINAL, 1, false);
+#undef SESRQ_GO
 }
 
 template <int KS>
@@ -791,27 +1045,25 @@ static int launch_ns(int ns, const LayerConst& c, const CUtensorMap& tmap, const
   return launch_epi<KS, 4, 8>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
 }
 
-// Tile height and stage count: maximise (SM load balance of the static round-robin schedule) x (halo
-// efficiency), subject to >= 2 (preferably >= 3) tile buffers fitting next to the fixed shared memory.
-struct TilePlan { int TH, tiles_y, stages; };
-static TilePlan choose_tiling(int H, int B, int tiles_x, int pad, size_t row_bytes, size_t slack_bytes,
-                              size_t per_row_extra, size_t fixed, int sms) {
-  TilePlan best{0, 0, 0};
-  double best_score = -1.0;
+// Tile height = TB * nbw rows (nbw issuer warps / row bands).  More bands = more MMA issue bandwidth but (k - 1)
+// extra edge rows per band; the accumulator ring (512 / (16 ns) row slots) must hold at least one tile.  Pick the
+// largest nbw <= the preferred one whose tile buffers fit at least twice next to the fixed shared memory.
+struct TilePlan { int TH, tiles_y, stages, nbw; size_t stage_bytes; };
+static TilePlan choose_tiling(int H, int ns, int k, int pad, size_t row_bytes, size_t slack_bytes, size_t per_row_extra,
+                              size_t fixed) {
+  const int nslot = TMEM_COLS / (16 * ns);
+  int want = (ns == 1) ? (k == 3 ? 3 : 2) : 1;
+  if (const char* e = getenv("SESRQ_UMMA_NBW")) want = atoi(e);                  // tuning experiments
+  want = std::max(1, std::min(want, std::min(3, nslot / TB)));
   const size_t total = 227 * 1024;
-  for (int th = std::min(H, 32); th >= 1; --th) {
-    const int ty = cdiv(H, th);
-    const int TH = cdiv(H, ty);                       // balanced rows per tile
+  TilePlan best{0, 0, 0, 0, 0};
+  for (int nbw = want; nbw >= 1; --nbw) {
+    const int TH = TB * nbw;
     const size_t stage = ((size_t)(TH + 2 * pad) * row_bytes + slack_bytes + 1023) & ~(size_t)1023;
     const size_t extra = (size_t)(TH + 2 * pad) * per_row_extra + 256;
     if (fixed + extra + 2 * stage > total) continue;
-    const int stages = (int)std::min<size_t>(MAX_STAGES, (total - fixed - extra) / stage);
-    const long long tiles = (long long)tiles_x * ty * B;
-    const double balance = (double)tiles / ((double)sms * (double)((tiles + sms - 1) / sms));
-    const double halo = 1.0 - 0.3 * (2.0 * pad) / (TH + 2.0 * pad);
-    const double depth = stages >= 3 ? 1.0 : 0.9;
-    const double score = balance * halo * depth;
-    if (score > best_score + 1e-9) { best_score = score; best = {TH, ty, stages}; }
+    best = {TH, cdiv(H, TH), (int)std::min<size_t>(MAX_STAGES, (total - fixed - extra) / stage), nbw, stage};
+    break;
   }
   return best;
 }
@@ -820,29 +1072,42 @@ static void fill_epilogue_params(UmmaParams& P, const LayerConst& c, int ns) {
   const bool natural = (c.epi == EPI_FINAL);
   for (int n = 0; n < 16; ++n) {
     const int co = natural ? n : chan_of_byte(n);
-    if (co >= c.cout) continue;
-    P.c_fused[n] = c.fused_const[co];
-    P.c_k[n] = c.add_const[co];
-    int sum = 0;
-    for (int p = 0; p < 4; ++p) {
-      P.c_pe[p][n] = c.pe_corr[p][co];
-      sum += c.pe_corr[p][co];
+    if (co >= c.cout) {                       // unused column: keep the float-bits form valid
+      if (ns <= 2) P.c_init[0][n] = MAGIC_BITS;
+      P.c_kmagic[n] = MAGIC_BITS;
+      continue;
     }
-    P.c_sum[n] = sum;
-    if (ns == 2 && c.pe_risky[co] >= 0) {
-      P.c_x[n] = c.pe_corr[c.pe_risky[co]][co];
-      P.xmask |= 1u << n;
+    if (ns <= 2) {
+      P.c_init[0][n] = c.fused_const[co] + MAGIC_BITS;        // sum_p pe_corr + K, as float bits
+    } else {
+      for (int p = 0; p < 4; ++p) P.c_init[p][n] = c.pe_corr[p][co];
+      P.c_kmagic[n] = c.add_const[co] + MAGIC_BITS;
+    }
+  }
+  if (ns == 2) {
+    int cols[16], chans[16], pes[16];
+    P.n_risky = risky_pairs(c, natural, cols, chans, pes);
+    for (int j = 0; j < P.n_risky; ++j) {
+      P.risky_col[j] = cols[j];
+      P.c_init[1][j] = c.pe_corr[pes[j]][chans[j]];
     }
   }
   P.lo_acc = c.lo_acc; P.hi_acc = c.hi_acc; P.lo_add = c.lo_add; P.hi_add = c.hi_add;
-  P.mf = c.mf; P.z_next = c.z_next; P.res_mf = c.res_mf; P.z_res = c.z_res; P.s_out = c.s_out;
+  P.mf = c.mf;
+  P.nbias = (float)(-12582912.0 * (double)c.mf);              // exact: 3 * M16 * 2^(22 - n)
+  P.z_next = c.z_next;
+  P.res_mf = c.res_mf;
+  P.res_nbias = (float)(-12582912.0 * (double)c.res_mf);
+  P.z_res = c.z_res;
+  P.s_out = c.s_out;
+  P.out_off = -(12582912.f + c.z_next);
   P.relu = c.relu; P.cout = c.cout;
 }
 
-template <int KS, int NS, int CIN, int EPI_WARPS>
+template <int KS, int NS, int CIN, bool FLOOR, int EPI_WARPS>
 static int launch_l0_one(const UmmaParams& P, const LayerDev& L, const float* d_x, uint8_t* d_out, int grid, size_t smem,
                          cudaStream_t st) {
-  auto kern = conv_umma_l0_kernel<KS, NS, CIN, EPI_WARPS>;
+  auto kern = conv_umma_l0_kernel<KS, NS, CIN, FLOOR, EPI_WARPS>;
   static bool attr_set = false;
   if (!attr_set) {
     SESRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -861,23 +1126,24 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
   memset(&P, 0, sizeof(P));
   P.tiles_x = cdiv(W, UMMA_M - 2 * pad);
   P.TW = cdiv(W, P.tiles_x);
-  const uint32_t w_bytes = (uint32_t)c.k * 2 * N * 16;
+  const uint32_t w_bytes = (uint32_t)2 * c.k * N * 16;
   const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (2 * MAX_STAGES + 2 * (TMEM_COLS / N)) + 64 + 1024;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const TilePlan tp = choose_tiling(H, B, P.tiles_x, pad, (size_t)L0_EP * 16, 8 * 16, (size_t)L0_SP * 4, fixed, sms);
+  const TilePlan tp = choose_tiling(H, ns, c.k, pad, (size_t)L0_EP * 16, 8 * 16, (size_t)L0_SP * 4, fixed);
   if (tp.stages < 2) return SESRQ_EUNSUPPORTED;
   P.TH = tp.TH;
   P.tiles_y = tp.tiles_y;
   P.stages = tp.stages;
-  P.stage_bytes = (uint32_t)((((size_t)(P.TH + 2 * pad) * L0_EP + 8) * 16 + 1023) & ~(size_t)1023);
+  P.nbw = tp.nbw;
+  P.stage_bytes = (uint32_t)tp.stage_bytes;
   const size_t smem = (size_t)P.stages * P.stage_bytes + (((size_t)(P.TH + 2 * pad) * L0_SP * 4 + 127) & ~(size_t)127) + fixed;
   if (smem > 227 * 1024) return SESRQ_EUNSUPPORTED;
   P.w_bytes = w_bytes;
   P.num_tiles = P.tiles_x * P.tiles_y * B;
   P.B = B; P.H = H; P.W = W; P.pad = pad;
-  P.idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
+  P.idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(UMMA_M >> 4) << 24);      // N is OR-ed in per instruction
   fill_epilogue_params(P, c, ns);
   P.cin = c.cin;
   P.pad_word = 0;
@@ -885,11 +1151,16 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
   P.in_scale = c.in_scale;
   P.in_zero = c.in_zero;
   const int grid = std::min(P.num_tiles, sms);
-#define SESRQ_L0_NS(KS_, CIN_)                                                                   \
-  do {                                                                                           \
-    if (ns == 1) return launch_l0_one<KS_, 1, CIN_, 16>(P, L, d_x, d_out, grid, smem, st);       \
-    if (ns == 2) return launch_l0_one<KS_, 2, CIN_, 16>(P, L, d_x, d_out, grid, smem, st);       \
-    return launch_l0_one<KS_, 4, CIN_, 8>(P, L, d_x, d_out, grid, smem, st);                     \
+#define SESRQ_L0_NS(KS_, CIN_)                                                                              \
+  do {                                                                                                      \
+    if (needs_floor(c)) {                                                                                   \
+      if (ns == 1) return launch_l0_one<KS_, 1, CIN_, true, 16>(P, L, d_x, d_out, grid, smem, st);          \
+      if (ns == 2) return launch_l0_one<KS_, 2, CIN_, true, 16>(P, L, d_x, d_out, grid, smem, st);          \
+      return launch_l0_one<KS_, 4, CIN_, true, 8>(P, L, d_x, d_out, grid, smem, st);                        \
+    }                                                                                                       \
+    if (ns == 1) return launch_l0_one<KS_, 1, CIN_, false, 16>(P, L, d_x, d_out, grid, smem, st);           \
+    if (ns == 2) return launch_l0_one<KS_, 2, CIN_, false, 16>(P, L, d_x, d_out, grid, smem, st);           \
+    return launch_l0_one<KS_, 4, CIN_, false, 8>(P, L, d_x, d_out, grid, smem, st);                         \
   } while (0)
 #define SESRQ_L0_CASE(KS_)                                                                       \
   do {                                                                                           \
@@ -920,32 +1191,30 @@ int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, c
   memset(&P, 0, sizeof(P));
   P.tiles_x = cdiv(W, UMMA_M - 2 * pad);
   P.TW = cdiv(W, P.tiles_x);
-  const int taps = c.k * c.k, pairs = (taps + 1) / 2;
-  const uint32_t w_bytes = (uint32_t)pairs * 2 * N * 16;
+  const int pairs = (c.k + 1) / 2;
+  const uint32_t w_bytes = (uint32_t)pairs * 2 * c.k * N * 16;
   const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (2 * MAX_STAGES + 2 * (TMEM_COLS / N)) + 64 + 1024;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const TilePlan tp = choose_tiling(H, B, P.tiles_x, pad, (size_t)UMMA_M * 16, (size_t)2 * pad * 16, 0, fixed, sms);
+  // slack: the last row's rightmost K chunk reaches 2*pad + 1 pixels past the row
+  // slack: the last row's rightmost K chunk reaches 2*pad + 1 pixels past the row
+  const TilePlan tp = choose_tiling(H, ns, c.k, pad, (size_t)UMMA_M * 16, (size_t)(2 * pad + 1) * 16, 0, fixed);
   if (tp.stages < 2) return SESRQ_EUNSUPPORTED;
   P.TH = tp.TH;
   P.tiles_y = tp.tiles_y;
   P.stages = tp.stages;
-  P.stage_bytes = (uint32_t)((((size_t)(P.TH + 2 * pad) * UMMA_M + 2 * pad) * 16 + 1023) & ~(size_t)1023);
+  P.nbw = tp.nbw;
+  P.stage_bytes = (uint32_t)tp.stage_bytes;
   P.box_bytes = (uint32_t)((P.TH + 2 * pad) * UMMA_M * 16);
   P.w_bytes = w_bytes;
   P.num_tiles = P.tiles_x * P.tiles_y * B;
   P.B = B; P.H = H; P.W = W; P.pad = pad;
-  for (int pr = 0; pr < pairs; ++pr) {
-    const int t0 = 2 * pr, t1 = 2 * pr + 1;
-    const int o0 = (t0 / c.k) * UMMA_M + (t0 % c.k);
-    const int o1 = (t1 < taps) ? (t1 / c.k) * UMMA_M + (t1 % c.k) : o0 + 1;   // dummy half: weights are zero
-    P.pair_off[pr] = o0;
-    P.pair_lbo[pr] = o1 - o0;
-  }
-  // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32, A = u8, B = s8, K-major both, N, M = 128
-  P.idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
+  // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32, A = u8, B = s8, K-major both, M = 128;
+  // N is OR-ed in per instruction (mma_issue_tile)
+  P.idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(UMMA_M >> 4) << 24);
   fill_epilogue_params(P, c, ns);
+  if (const char* e = getenv("SESRQ_UMMA_DBG")) P.dbg = atoi(e);
 
   // ---- tensor map over the NHWC16 input viewed as (W*2 x 8-byte, H, B) ----
   CUtensorMap tmap;
