@@ -55,23 +55,34 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Waiting warps share their scheduler with working ones and a spinning warp is always "ready", so a plain try_wait
+// loop steals issue slots (ncu: 150 M of 510 M instructions of the layer-0 kernel were such spins and the operand
+// builders ran at 0.1 IPC).  The suspend-time hint parks the warp in hardware until the phase completes (or the hint
+// expires), with no blind sleep on the critical path.
+constexpr uint32_t MBAR_SUSPEND_NS = 200000;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t a = smem_u32(bar);
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
-      "}\n" ::"r"(a), "r"(parity)
+      "}\n" ::"r"(a), "r"(parity), "r"(MBAR_SUSPEND_NS)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -129,6 +140,39 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const int (&r)[16]) {
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): two IEEE round-to-nearest operations per issue slot, each lane
+// bit-identical to the scalar instruction.  The scalar operands are broadcast by the hardware.
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float2 f2_unpack(uint64_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ float2 f2_fma(float2 a, float b, float c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b, b)), "l"(f2_pack(c, c)));
+  return f2_unpack(r);
+}
+__device__ __forceinline__ float2 f2_fma3(float2 a, float2 b, float2 c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)), "l"(f2_pack(c.x, c.y)));
+  return f2_unpack(r);
+}
+__device__ __forceinline__ float2 f2_add(float2 a, float b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b, b)));
+  return f2_unpack(r);
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b, b)));
+  return f2_unpack(r);
+}
 
 // bytes [a,b,c,d] (a lowest) of the four ints saturated to int8: two I2IP instructions.
 // PTX: cvt.pack.sat.s8.s32.b32 d, x, y, z  ->  d = (z << 16) | (sat8(x) << 8) | sat8(y)
@@ -201,6 +245,9 @@ struct UmmaParams {
   int32_t cin;
   uint32_t pad_word;                     // out-of-frame pixel: byte c = z' + 128 for c < cin
   float in_scale, in_zero;
+  int32_t x_tma;                         // 1: fp32 input tiles arrive by TMA (needs W % 4 == 0), 0: builders read global memory
+  int32_t xstages;                       // fp32 tile buffers in flight (2..L0_XSTAGES)
+  uint32_t xstage_bytes;                 // one fp32 tile buffer: cin planes of (TH + 2 pad) rows x L0_XP floats
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -228,20 +275,24 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
       }
     }
   }
-  float yv[16];
+  float2 yv[8];                                        // channel pairs (2k, 2k+1)
 #pragma unroll
-  for (int n = 0; n < 16; ++n) {
-    int m;
-    if (NS <= 2) {
-      m = acc[0][n];
-    } else {
-      int s = 0;
+  for (int k = 0; k < 8; ++k) {
+    int m[2];
 #pragma unroll
-      for (int p = 0; p < NS; ++p) s += clampi(acc[p][n], P.lo_acc, P.hi_acc);
-      m = clampi(s, P.lo_add, P.hi_add) + P.c_kmagic[n];
+    for (int h = 0; h < 2; ++h) {
+      const int n = 2 * k + h;
+      if (NS <= 2) {
+        m[h] = acc[0][n];
+      } else {
+        int s = 0;
+#pragma unroll
+        for (int p = 0; p < NS; ++p) s += clampi(acc[p][n], P.lo_acc, P.hi_acc);
+        m[h] = clampi(s, P.lo_add, P.hi_add) + P.c_kmagic[n];
+      }
     }
-    yv[n] = __fmaf_rn(__int_as_float(m), P.mf, P.nbias);                          // RN(A * M16 * 2^-n)  (:529)
-    if (FLOOR) yv[n] = fmaxf(yv[n], relu_floor);
+    yv[k] = f2_fma(make_float2(__int_as_float(m[0]), __int_as_float(m[1])), P.mf, P.nbias);   // RN(A * M16 * 2^-n)  (:529)
+    if (FLOOR) { yv[k].x = fmaxf(yv[k].x, relu_floor); yv[k].y = fmaxf(yv[k].y, relu_floor); }
   }
   if (EPI == EPI_FINAL) {
     // q5 = clamp(rint(y + z5)); out = (q5 - z5) * s5 (:585,:594); columns are in natural channel order.
@@ -249,23 +300,31 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
     constexpr int R2 = RS * RS;
     const long long HrWr = HW * R2;
     const int Wr = P.W * RS;
+    float o[16];
 #pragma unroll
-    for (int n0 = 0; n0 < 16; n0 += RS) {
-      if (n0 < P.cout) {
-        float o[RS];
-#pragma unroll
-        for (int j = 0; j < RS; ++j) {
-          float t = __fadd_rn(yv[n0 + j], P.z_next);
-          t = fminf(fmaxf(t, -128.f), 127.f);
-          const float rm = __fadd_rn(t, MAGIC_F);
-          if (qb) qb[(long long)(n0 + j) * HW] = (int8_t)__float_as_int(rm);
-          o[j] = __fmul_rn(__fadd_rn(rm, P.out_off), P.s_out);
+    for (int k = 0; k < 8; ++k) {
+      if (2 * k < P.cout) {
+        float2 t = f2_add(yv[k], P.z_next);
+        t.x = fminf(fmaxf(t.x, -128.f), 127.f);
+        t.y = fminf(fmaxf(t.y, -128.f), 127.f);
+        const float2 rm = f2_add(t, MAGIC_F);
+        if (qb) {
+          qb[(long long)(2 * k) * HW] = (int8_t)__float_as_int(rm.x);
+          if (2 * k + 1 < P.cout) qb[(long long)(2 * k + 1) * HW] = (int8_t)__float_as_int(rm.y);
         }
-        if (yb) {
+        const float2 ov = f2_mul(f2_add(rm, P.out_off), P.s_out);
+        o[2 * k] = ov.x;
+        o[2 * k + 1] = ov.y;
+      }
+    }
+    if (yb) {
+#pragma unroll
+      for (int n0 = 0; n0 < 16; n0 += RS) {
+        if (n0 < P.cout) {
           float* dst = yb + (long long)(n0 / R2) * HrWr + (long long)((n0 % R2) / RS) * Wr;
-          if constexpr (RS == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-          else if constexpr (RS == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
-          else *dst = o[0];
+          if constexpr (RS == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[n0], o[n0 + 1], o[n0 + 2], o[n0 + 3]);
+          else if constexpr (RS == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[n0], o[n0 + 1]);
+          else *dst = o[n0];
         }
       }
     }
@@ -277,33 +336,30 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
     const uint32_t scw[4] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-      int ic[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ic[j] = __float2int_rn(__fadd_rn(yv[4 * w + j], -128.f));
-      const uint32_t vic = pack4_sat_s8(ic[0], ic[1], ic[2], ic[3]) ^ 0x80808080u;
+      const float2 u0 = f2_add(yv[2 * w], -128.f), u1 = f2_add(yv[2 * w + 1], -128.f);
+      const uint32_t vic = pack4_sat_s8(__float2int_rn(u0.x), __float2int_rn(u0.y), __float2int_rn(u1.x), __float2int_rn(u1.y)) ^
+                           0x80808080u;
       // 16-bit lanes: even bytes and odd bytes
       const uint32_t s_even = (scw[w] & 0x00ff00ffu) + (vic & 0x00ff00ffu);
       const uint32_t s_odd = __byte_perm(scw[w], 0u, 0x4341u) + __byte_perm(vic, 0u, 0x4341u);
-      int q[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t lane16 = (j & 1) ? s_odd : s_even;
-        // bits of the float 12582912 + S: low two bytes from the 16-bit lane, high two from the magic constant
-        const uint32_t mb = __byte_perm(lane16, (uint32_t)MAGIC_BITS, (j & 2) ? 0x7632u : 0x7610u);
-        const float tt = __fmaf_rn(__uint_as_float(mb), P.res_mf, P.res_nbias);
-        q[j] = __float2int_rn(__fadd_rn(tt, P.z_res));
-      }
-      ow[w] = pack4_sat_s8(q[0], q[1], q[2], q[3]) ^ 0x80808080u;
+      // bits of the float 12582912 + S: low two bytes from the 16-bit lane, high two from the magic constant
+      const float2 m01 = make_float2(__uint_as_float(__byte_perm(s_even, (uint32_t)MAGIC_BITS, 0x7610u)),
+                                     __uint_as_float(__byte_perm(s_odd, (uint32_t)MAGIC_BITS, 0x7610u)));
+      const float2 m23 = make_float2(__uint_as_float(__byte_perm(s_even, (uint32_t)MAGIC_BITS, 0x7632u)),
+                                     __uint_as_float(__byte_perm(s_odd, (uint32_t)MAGIC_BITS, 0x7632u)));
+      const float2 t01 = f2_add(f2_fma(m01, P.res_mf, P.res_nbias), P.z_res);
+      const float2 t23 = f2_add(f2_fma(m23, P.res_mf, P.res_nbias), P.z_res);
+      ow[w] = pack4_sat_s8(__float2int_rn(t01.x), __float2int_rn(t01.y), __float2int_rn(t23.x), __float2int_rn(t23.y)) ^
+              0x80808080u;
     }
     *out_px = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   } else {
     uint32_t ow[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-      int q[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) q[j] = __float2int_rn(__fadd_rn(yv[4 * w + j], P.z_next));   // :280, clamped by the pack
-      ow[w] = pack4_sat_s8(q[0], q[1], q[2], q[3]) ^ 0x80808080u;                                // v = q + 128
+      const float2 t0 = f2_add(yv[2 * w], P.z_next), t1 = f2_add(yv[2 * w + 1], P.z_next);     // :280, clamped by the pack
+      ow[w] = pack4_sat_s8(__float2int_rn(t0.x), __float2int_rn(t0.y), __float2int_rn(t1.x), __float2int_rn(t1.y)) ^
+              0x80808080u;                                                                      // v = q + 128
     }
     *out_px = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
@@ -360,7 +416,6 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
   constexpr int NSLOT = TMEM_COLS / NCOLS;
   constexpr int NWG = EPI_WARPS / 4;
   constexpr int RG = GroupRows<NS>::value;
-  static_assert(NSLOT % NWG == 0, "initial slot pre-load is dealt round-robin to the warpgroups");
   const int wg = ewarp >> 2;                    // warpgroup
   const int quarter = ewarp & 3;                // TMEM lane quarter this warp may access (== warp id % 4)
   const int ox = quarter * 32 + lane;           // pitch == UMMA_M: a slot is one output row of the tile, lane is the column
@@ -420,13 +475,7 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
           tmem_ld_wait();
           slot_fence<NS>(acc[i & 1]);
           if (i + 1 < RG && i + 1 < cnt) slot_load<NS>(tq + slot * NCOLS, acc[(i + 1) & 1]);   // next row in flight
-          if (!(P.dbg & 2)) {
-            slot_store<NS>(taddr, cinit);
-            tmem_st_wait();
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[slot_cur]);
+          if (!(P.dbg & 2)) slot_store<NS>(taddr, cinit);       // re-arm the slot; completion is awaited after the math
 
           if (valid && !(P.dbg & 1)) {
             const int mb = mb0 + i;
@@ -440,6 +489,9 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
             }
             epilogue_pixel<NS, EPI, RS, FLOOR>(P, acc[i & 1], sc[i], out + pix, qb, yb, HW, relu_floor);
           }
+          tmem_st_wait();                  // warp-collective: every lane's re-arm store has landed
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&acc_empty[slot_cur]);
         }
       }
     }
@@ -533,7 +585,14 @@ __device__ __forceinline__ void mma_issue_band(const int bw, const int lane, con
   // ---- all TB slots of the band pre-loaded?  (lane l <-> band row l) ----
   {
     const uint32_t bar = acc_empty_addr + (slot0 + (uint32_t)(lane & (TB - 1))) * 8u;
-    while (!__all_sync(0xffffffffu, mbar_test(bar, ring.par) != 0u)) {}
+    uint32_t ok;
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(ok) : "r"(bar), "r"(ring.par), "r"(MBAR_SUSPEND_NS) : "memory");
+    } while (!__all_sync(0xffffffffu, ok != 0u));
     tc_fence_after();
     // rows the tile does not have: nobody will consume their slot, so complete its phase here (4 = arrivals of a
     // consuming warpgroup); the slot stays pre-loaded
@@ -680,6 +739,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 constexpr int L0_EP = 132;               // E row pitch in entries (X up to 127 + 4)
 constexpr int L0_SP = 136;               // S row pitch in words  (X + 3 up to 134)
 constexpr int L0_BUILD_WARPS = 8;
+constexpr int L0_XP = 136;               // fp32 tile row pitch in floats = TMA box width: 132 pixels + up to 3 of alignment
+                                         // (the box must start on a 16-byte boundary: an unaligned inner coordinate faults)
+constexpr int L0_XSTAGES = 4;            // fp32 tile buffers (upper bound; P.xstages are used)
+constexpr int L0_CHUNK = 29;             // operand entries one builder warp pass produces (32 pixels - 3 neighbours)
 
 // x / s with a hoisted reciprocal.  `rcp` is the Newton-refined reciprocal of s; the three operations are
 // exactly the quotient steps of div.rn.f32's fast path (q0 = x*rcp; e = fma(-s, q0, x); q = fma(rcp, e, q0)),
@@ -702,28 +765,42 @@ struct ExactDiv {
     const float e = __fmaf_rn(-s, q0, x);
     return __fmaf_rn(rcp, e, q0);
   }
+  // two quotients per instruction (FMUL2 / FFMA2): lane-wise identical to the scalar sequence
+  __device__ __forceinline__ float2 operator()(float2 x) const {
+    x.x = fminf(fmaxf(x.x, -lim), lim);
+    x.y = fminf(fmaxf(x.y, -lim), lim);
+    const float2 q0 = f2_mul(x, rcp);
+    const float2 e = f2_fma3(make_float2(-s, -s), q0, x);
+    return f2_fma3(make_float2(rcp, rcp), e, q0);
+  }
 };
 
 template <int KS, int NS, int CIN, bool FLOOR, int EPI_WARPS>
 __global__ void __launch_bounds__((CTRL_WARPS + EPI_WARPS + L0_BUILD_WARPS) * 32, 1)
-conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restrict__ w_img,
-                    const float* __restrict__ x, uint4* __restrict__ out) {
+conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ UmmaParams P,
+                    const uint8_t* __restrict__ w_img, const float* __restrict__ x, uint4* __restrict__ out) {
   constexpr int NCOLS = 16 * NS;
   constexpr int NSLOT = TMEM_COLS / NCOLS;
   constexpr int PAD = (KS - 1) / 2;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* const e0 = smem;                                         // E planes: P.stages buffers of stage_bytes
-  uint32_t* const s_plane = reinterpret_cast<uint32_t*>(smem + (size_t)P.stages * P.stage_bytes);
+  // second region: the fp32 tile buffers (TMA path) or the S plane (fallback path)
+  uint8_t* const region2 = smem + (size_t)P.stages * P.stage_bytes;
+  uint32_t* const s_plane = reinterpret_cast<uint32_t*>(region2);
   const uint32_t s_bytes = (uint32_t)(((P.TH + 2 * PAD) * L0_SP * 4 + 127) & ~127);
-  uint8_t* const w_s = smem + (size_t)P.stages * P.stage_bytes + s_bytes;
+  const uint32_t r2_bytes = P.x_tma ? (uint32_t)P.xstages * P.xstage_bytes : s_bytes;
+  uint8_t* const w_s = region2 + r2_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + ((P.w_bytes + 127) & ~127u));
   uint64_t* e_full = bars;                               // [MAX_STAGES] count = builder warps
   uint64_t* e_empty = bars + MAX_STAGES;                 // [MAX_STAGES] count = MMA warps (tcgen05.commit)
   uint64_t* acc_full = bars + 2 * MAX_STAGES;
   uint64_t* acc_empty = bars + 2 * MAX_STAGES + NSLOT;
-  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * NSLOT);
+  uint64_t* x_full = bars + 2 * MAX_STAGES + 2 * NSLOT;  // [L0_XSTAGES] TMA transaction barriers
+  uint64_t* x_empty = x_full + L0_XSTAGES;               // [L0_XSTAGES] count = builder warps
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(x_empty + L0_XSTAGES);
 
+  __shared__ uint32_t stage_w[L0_BUILD_WARPS][4][32];       // builders: one row of pixel words per pass in flight
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -731,6 +808,7 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
     reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(w_img) + i);
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
+    if (P.x_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&xmap)) : "memory");
     for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(&e_full[i], L0_BUILD_WARPS);
       mbar_init(&e_empty[i], P.nbw);
@@ -738,6 +816,10 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);
+    }
+    for (int i = 0; i < L0_XSTAGES; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], L0_BUILD_WARPS);
     }
     fence_barrier_init();
   }
@@ -750,7 +832,22 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
   const long long HW = (long long)P.H * P.W;
 
   if (warp == 0) {
-    // idle (no TMA in this kernel: the operand plane is computed, not copied)
+    // ================= TMA producer: fp32 halo tiles, one box of (L0_XP, TH + 2 pad, CIN) per tile.  Out-of-frame
+    // elements are zero-filled, and x = 0 quantises to max(z0, -128), the reference's pad code (:351-352) =========
+    if (P.x_tma && lane == 0) {
+      int xs = 0;
+      uint32_t xph = 0;
+      for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+        if (P.dbg & 512) break;
+        mbar_wait(&x_empty[xs], xph ^ 1);
+        const int b = t / tiles_per_frame;
+        const int r = t - b * tiles_per_frame;
+        const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
+        mbar_arrive_expect_tx(&x_full[xs], (uint32_t)(CIN * (P.TH + 2 * PAD) * L0_XP * 4));
+        tma_load_4d(region2 + (size_t)xs * P.xstage_bytes, &xmap, (tx * P.TW - PAD) & ~3, ty * P.TH - PAD, 0, b, &x_full[xs]);
+        if (++xs == P.xstages) { xs = 0; xph ^= 1; }
+      }
+    }
   } else if (warp < CTRL_WARPS) {
     // ================= MMA issuer warps 1 .. nbw =================
     const int bw = warp - 1;
@@ -790,6 +887,82 @@ conv_umma_l0_kernel(const __grid_constant__ UmmaParams P, const uint8_t* __restr
     const float z0 = P.in_zero;
     int st = 0;
     uint32_t ph = 0;
+    if (P.x_tma) {
+      // ---- TMA path: every warp pass turns 32 consecutive pixels of one tile row (read from the fp32 tile in shared
+      // memory) into L0_CHUNK operand entries E[row][X] = (w(X), w(X+1), w(X+2), w(X+3)); the neighbours' words come by
+      // warp shuffle, consecutive passes overlap by 3 pixels.  Two passes are computed together on packed pairs. ----
+      constexpr int NCH = (L0_EP + L0_CHUNK - 1) / L0_CHUNK;          // passes per row
+      const int bwid = bt >> 5;
+      const int rp = P.TH + 2 * PAD;                                   // rows per fp32 plane
+      int xs = 0;
+      uint32_t xph = 0;
+      for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+        const int r = t % tiles_per_frame;
+        const int rows = min(P.TH, P.H - (r / P.tiles_x) * P.TH) + 2 * PAD;
+        const int delta = ((r % P.tiles_x) * P.TW - PAD) & 3;          // pixels the aligned box starts early
+        if (lane == 0) {
+          if (!(P.dbg & 512)) mbar_wait(&x_full[xs], xph);
+          mbar_wait(&e_empty[st], ph ^ 1);                             // the MMAs that read this E stage have retired
+        }
+        __syncwarp();
+        const float* xsrc = reinterpret_cast<const float*>(region2 + (size_t)xs * P.xstage_bytes);
+        uint4* e = reinterpret_cast<uint4*>(e0 + (size_t)st * P.stage_bytes);
+        const int items = (P.dbg & 256) ? 0 : rows * NCH;
+        // 4 passes per iteration (independent dependency chains: the builders are latency-bound), no lane-divergent
+        // branch anywhere: out-of-range passes / pixels are clamped to valid addresses and only the store is predicated
+        constexpr int UB = 4;
+        for (int it = bwid; it < items; it += UB * L0_BUILD_WARPS) {
+          int eidx[UB];
+          bool ok[UB];
+          float v[UB][CIN];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int item = it + u * L0_BUILD_WARPS;
+            const int itc = min(item, items - 1);
+            const int row = itc / NCH;
+            const int X = (itc - row * NCH) * L0_CHUNK + lane;
+            ok[u] = item < items && lane < L0_CHUNK && X < L0_EP;
+            eidx[u] = row * L0_EP + X;
+            const int xl = min(X + delta, L0_XP - 1);                  // X >= 132 only feeds "don't care" bytes
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) v[u][c] = xsrc[(c * rp + row) * L0_XP + xl];
+          }
+          uint32_t w0[UB];
+#pragma unroll
+          for (int u = 0; u < UB; u += 2) {
+            int q[2][4] = {{-128, -128, -128, -128}, {-128, -128, -128, -128}};   // unused channels: byte 0 (zero weights)
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+              const float2 tq = f2_add(div_s0(make_float2(v[u][c], v[u + 1][c])), z0);   // :225, clamped by the pack
+              q[0][c] = __float2int_rn(tq.x);
+              q[1][c] = __float2int_rn(tq.y);
+            }
+            w0[u] = pack4_sat_s8(q[0][0], q[0][1], q[0][2], q[0][3]) ^ 0x80808080u;
+            w0[u + 1] = pack4_sat_s8(q[1][0], q[1][1], q[1][2], q[1][3]) ^ 0x80808080u;
+          }
+          // neighbours' words through a per-warp staging row in shared memory (warp shuffles were measured ~5x slower
+          // here: 0.27 ms of a 0.60 ms kernel)
+#pragma unroll
+          for (int u = 0; u < UB; ++u) stage_w[bwid][u][lane] = w0[u];
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const uint32_t* sw = stage_w[bwid][u];
+            const uint32_t w1 = sw[min(lane + 1, 31)], w2 = sw[min(lane + 2, 31)], w3 = sw[min(lane + 3, 31)];
+            if (ok[u]) e[eidx[u]] = make_uint4(w0[u], w1, w2, w3);
+          }
+          __syncwarp();
+        }
+        fence_proxy_async();                                           // generic-proxy stores -> visible to UMMA
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&e_full[st]);
+          mbar_arrive(&x_empty[xs]);
+        }
+        if (++st == P.stages) { st = 0; ph ^= 1; }
+        if (++xs == P.xstages) { xs = 0; xph ^= 1; }
+      }
+    } else
     for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
       const int b = t / tiles_per_frame;
       const int r = t - b * tiles_per_frame;
@@ -1040,7 +1213,11 @@ template <int KS>
 static int launch_ns(int ns, const LayerConst& c, const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L,
                      const uint8_t* d_shortcut, uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem,
                      cudaStream_t st) {
-  if (ns == 1) return launch_epi<KS, 1, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+  if (ns == 1) {
+    static const int epi_warps = getenv("SESRQ_UMMA_EPI_WARPS") ? atoi(getenv("SESRQ_UMMA_EPI_WARPS")) : 16;   // tuning
+    if (epi_warps == 24) return launch_epi<KS, 1, 24>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+    return launch_epi<KS, 1, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+  }
   if (ns == 2) return launch_epi<KS, 2, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
   return launch_epi<KS, 4, 8>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
 }
@@ -1052,7 +1229,7 @@ struct TilePlan { int TH, tiles_y, stages, nbw; size_t stage_bytes; };
 static TilePlan choose_tiling(int H, int ns, int k, int pad, size_t row_bytes, size_t slack_bytes, size_t per_row_extra,
                               size_t fixed) {
   const int nslot = TMEM_COLS / (16 * ns);
-  int want = (ns == 1) ? (k == 3 ? 3 : 2) : 1;
+  int want = (ns == 1) ? (k == 3 ? 3 : 2) : (ns == 2 ? 2 : 1);
   if (const char* e = getenv("SESRQ_UMMA_NBW")) want = atoi(e);                  // tuning experiments
   want = std::max(1, std::min(want, std::min(3, nslot / TB)));
   const size_t total = 227 * 1024;
@@ -1105,15 +1282,16 @@ static void fill_epilogue_params(UmmaParams& P, const LayerConst& c, int ns) {
 }
 
 template <int KS, int NS, int CIN, bool FLOOR, int EPI_WARPS>
-static int launch_l0_one(const UmmaParams& P, const LayerDev& L, const float* d_x, uint8_t* d_out, int grid, size_t smem,
-                         cudaStream_t st) {
+static int launch_l0_one(const CUtensorMap& xmap, const UmmaParams& P, const LayerDev& L, const float* d_x, uint8_t* d_out,
+                         int grid, size_t smem, cudaStream_t st) {
   auto kern = conv_umma_l0_kernel<KS, NS, CIN, FLOOR, EPI_WARPS>;
   static bool attr_set = false;
   if (!attr_set) {
-    SESRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // the kernel also has ~4.2 KB of static shared memory; static + dynamic <= 227 KB
+    SESRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 5 * 1024));
     attr_set = true;
   }
-  kern<<<grid, (CTRL_WARPS + EPI_WARPS + L0_BUILD_WARPS) * 32, smem, st>>>(P, L.d_wumma, d_x, reinterpret_cast<uint4*>(d_out));
+  kern<<<grid, (CTRL_WARPS + EPI_WARPS + L0_BUILD_WARPS) * 32, smem, st>>>(xmap, P, L.d_wumma, d_x, reinterpret_cast<uint4*>(d_out));
   SESRQ_LAUNCH_CHECK("conv_umma_l0_kernel");
   return SESRQ_OK;
 }
@@ -1127,19 +1305,53 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
   P.tiles_x = cdiv(W, UMMA_M - 2 * pad);
   P.TW = cdiv(W, P.tiles_x);
   const uint32_t w_bytes = (uint32_t)2 * c.k * N * 16;
-  const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (2 * MAX_STAGES + 2 * (TMEM_COLS / N)) + 64 + 1024;
+  // fixed part: weights, barriers, slack for alignment, and the kernel's 4 KB of static shared memory (stage_w)
+  const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (2 * MAX_STAGES + 2 * (TMEM_COLS / N) + 2 * L0_XSTAGES) + 64 + 1024 + 5 * 1024;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const TilePlan tp = choose_tiling(H, ns, c.k, pad, (size_t)L0_EP * 16, 8 * 16, (size_t)L0_SP * 4, fixed);
+  // fp32 tiles by TMA need 16-byte aligned rows (W % 4 == 0), a 16-byte aligned base, and x = 0 -> pad code (z0 <= 127)
+  EncodeTiledFn encode = get_encode_fn();
+  P.x_tma = (encode && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && c.in_zero <= 127.f) ? 1 : 0;
+  if (getenv("SESRQ_L0_NO_TMA")) P.x_tma = 0;
+  const size_t per_row_extra = P.x_tma ? (size_t)2 * c.cin * L0_XP * 4 : (size_t)L0_SP * 4;
+  const TilePlan tp = choose_tiling(H, ns, c.k, pad, (size_t)L0_EP * 16, 8 * 16, per_row_extra, fixed + 256);
   if (tp.stages < 2) return SESRQ_EUNSUPPORTED;
   P.TH = tp.TH;
   P.tiles_y = tp.tiles_y;
-  P.stages = tp.stages;
   P.nbw = tp.nbw;
   P.stage_bytes = (uint32_t)tp.stage_bytes;
-  const size_t smem = (size_t)P.stages * P.stage_bytes + (((size_t)(P.TH + 2 * pad) * L0_SP * 4 + 127) & ~(size_t)127) + fixed;
+  P.xstage_bytes = (uint32_t)(((size_t)c.cin * (P.TH + 2 * pad) * L0_XP * 4 + 127) & ~(size_t)127);
+  const size_t s_region = (((size_t)(P.TH + 2 * pad) * L0_SP * 4 + 127) & ~(size_t)127);
+  if (P.x_tma) {
+    // two operand-plane buffers suffice (built while the other is consumed); the fp32 tiles need depth to hide
+    // the HBM latency + transfer time of a tile behind the build of the previous ones
+    P.stages = 2;
+    const size_t room = 227 * 1024 - fixed - (size_t)P.stages * P.stage_bytes;
+    P.xstages = (int)std::min<size_t>(L0_XSTAGES, room / P.xstage_bytes);
+    if (const char* e = getenv("SESRQ_L0_XSTAGES")) P.xstages = std::min(P.xstages, std::max(2, atoi(e)));
+    if (P.xstages < 2) return SESRQ_EUNSUPPORTED;
+  } else {
+    P.stages = std::min(tp.stages, 3);
+  }
+  const size_t region2 = P.x_tma ? (size_t)P.xstages * P.xstage_bytes : s_region;
+  const size_t smem = (size_t)P.stages * P.stage_bytes + region2 + fixed;
   if (smem > 227 * 1024) return SESRQ_EUNSUPPORTED;
+  CUtensorMap xmap;
+  memset(&xmap, 0, sizeof(xmap));
+  if (P.x_tma) {
+    cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)c.cin, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)c.cin * H * W * 4};
+    cuuint32_t box[4] = {(cuuint32_t)L0_XP, (cuuint32_t)(P.TH + 2 * pad), (cuuint32_t)c.cin, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d_x), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (layer-0 input)");
+      return SESRQ_ECUDA;
+    }
+  }
   P.w_bytes = w_bytes;
   P.num_tiles = P.tiles_x * P.tiles_y * B;
   P.B = B; P.H = H; P.W = W; P.pad = pad;
@@ -1150,17 +1362,18 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
   for (int ci = 0; ci < c.cin; ++ci) P.pad_word |= (uint32_t)c.pad_byte << (8 * ci);
   P.in_scale = c.in_scale;
   P.in_zero = c.in_zero;
+  if (const char* e = getenv("SESRQ_UMMA_DBG")) P.dbg = atoi(e);
   const int grid = std::min(P.num_tiles, sms);
 #define SESRQ_L0_NS(KS_, CIN_)                                                                              \
   do {                                                                                                      \
     if (needs_floor(c)) {                                                                                   \
-      if (ns == 1) return launch_l0_one<KS_, 1, CIN_, true, 16>(P, L, d_x, d_out, grid, smem, st);          \
-      if (ns == 2) return launch_l0_one<KS_, 2, CIN_, true, 16>(P, L, d_x, d_out, grid, smem, st);          \
-      return launch_l0_one<KS_, 4, CIN_, true, 8>(P, L, d_x, d_out, grid, smem, st);                        \
+      if (ns == 1) return launch_l0_one<KS_, 1, CIN_, true, 16>(xmap, P, L, d_x, d_out, grid, smem, st);          \
+      if (ns == 2) return launch_l0_one<KS_, 2, CIN_, true, 16>(xmap, P, L, d_x, d_out, grid, smem, st);          \
+      return launch_l0_one<KS_, 4, CIN_, true, 8>(xmap, P, L, d_x, d_out, grid, smem, st);                        \
     }                                                                                                       \
-    if (ns == 1) return launch_l0_one<KS_, 1, CIN_, false, 16>(P, L, d_x, d_out, grid, smem, st);           \
-    if (ns == 2) return launch_l0_one<KS_, 2, CIN_, false, 16>(P, L, d_x, d_out, grid, smem, st);           \
-    return launch_l0_one<KS_, 4, CIN_, false, 8>(P, L, d_x, d_out, grid, smem, st);                         \
+    if (ns == 1) return launch_l0_one<KS_, 1, CIN_, false, 16>(xmap, P, L, d_x, d_out, grid, smem, st);           \
+    if (ns == 2) return launch_l0_one<KS_, 2, CIN_, false, 16>(xmap, P, L, d_x, d_out, grid, smem, st);           \
+    return launch_l0_one<KS_, 4, CIN_, false, 8>(xmap, P, L, d_x, d_out, grid, smem, st);                         \
   } while (0)
 #define SESRQ_L0_CASE(KS_)                                                                       \
   do {                                                                                           \
