@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--outputs", default="both", choices=["both", "y", "q5"],
+                    help="what the last layer materialises: fp32 pixel-shuffled y (sim.py:205), int8 q5 (input.5.pt), or both")
     args = ap.parse_args()
     case, H, W, defB = WORKLOADS[args.workload]
     B = args.batch or defB
@@ -182,8 +184,9 @@ def main():
     x_host = torch.rand(B, cin, H, W, generator=gen).pin_memory()
     x = x_host.to(dev, non_blocking=True)
     qs, ys = net.out_shapes(B, H, W)
-    q5 = torch.empty(qs, dtype=torch.int8, device=dev)
-    y = torch.empty(ys, dtype=torch.float32, device=dev)
+    want_q5, want_y = args.outputs in ("both", "q5"), args.outputs in ("both", "y")
+    q5 = torch.empty(qs, dtype=torch.int8, device=dev) if want_q5 else None
+    y = torch.empty(ys, dtype=torch.float32, device=dev) if want_y else None
 
     def barrier():
         if world > 1:
@@ -191,7 +194,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     for _ in range(max(args.warmup, 3)):
-        net(x, q5=q5, y=y)
+        net(x, want_q5=want_q5, want_y=want_y, q5=q5, y=y)
     barrier()
 
     # ---- timed region: K steps, inputs resident in HBM, per-kernel events on the launching stream ----
@@ -204,7 +207,7 @@ def main():
     barrier()
     e0.record()
     for _ in range(args.steps):
-        net(x, q5=q5, y=y)
+        net(x, want_q5=want_q5, want_y=want_y, q5=q5, y=y)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -227,7 +230,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    lbytes = layer_bytes_per_px(cin, cout)
+    lbytes = layer_bytes_per_px(cin, cout, want_q5, want_y)
     lr_px_launch = [(B * H * W * args.steps) / max(layer_launches[i], 1) for i in range(5)]
     per_layer = []
     for i in range(5):
@@ -251,8 +254,8 @@ def main():
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside) ----
     e2e = None
     if not args.no_e2e:
-        q5_h = torch.empty(qs, dtype=torch.int8).pin_memory()
-        y_h = torch.empty(ys, dtype=torch.float32).pin_memory()
+        q5_h = torch.empty(qs, dtype=torch.int8).pin_memory() if want_q5 else None
+        y_h = torch.empty(ys, dtype=torch.float32).pin_memory() if want_y else None
         net.forward_host(x_host, q5_h, y_h)
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -266,7 +269,7 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e_ms = float(te.item()) / args.e2e_steps
         e2e = {"value": world * B * out_px_frame / (e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
-               "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": q5_h.numel() + y_h.numel() * 4,
+               "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": (q5_h.numel() if want_q5 else 0) + (y_h.numel() * 4 if want_y else 0),
                "ms_per_step": e_ms, "api": "sesrq_net_forward_i8_host (Int8Net.forward_host), pinned host buffers"}
 
     cpu = None
@@ -282,7 +285,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload, "frames_per_gpu_per_step": B, "H": H, "W": W, "upscale": r,
-                       "cin": cin, "cout": cout, "outputs": "q5 int8 NCHW + fp32 pixel-shuffled y",
+                       "cin": cin, "cout": cout, "outputs": {"both": "q5 int8 NCHW + fp32 pixel-shuffled y", "y": "fp32 pixel-shuffled y", "q5": "q5 int8 NCHW"}[args.outputs],
                        "weights": "reference checkpoint collapsed (tests/golden/%s.npz), reference min/max thresholds" % case,
                        "input": "torch.rand seed 4321+rank, %.0f MB per step > 126 MB L2 (no L2 flush needed)" % (x.numel() * 4 / 1e6),
                        "parallelism": "dp%d frames sharded, no collective" % world},

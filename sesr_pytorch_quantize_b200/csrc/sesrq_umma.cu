@@ -275,6 +275,23 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
       }
     }
   }
+  if (NS == 1 && EPI == EPI_FINAL) {
+    // spare-column layout (host: spare_column_layout): columns 12 + j hold the risky partial sums
+    if (P.n_risky > 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= P.n_risky) break;
+        const int v = acc[0][12 + j];
+        const int d = clampi(v, P.lo_acc, P.hi_acc) - v;
+        if (d != 0) {
+          const int col = P.risky_col[j];
+#pragma unroll
+          for (int n = 0; n < 12; ++n)
+            if (n == col) acc[0][n] += d;
+        }
+      }
+    }
+  }
   float2 yv[8];                                        // channel pairs (2k, 2k+1)
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -1065,9 +1082,22 @@ bool umma_supported(const LayerConst& c) {
   return true;
 }
 
+// Final layers with <= 12 output channels leave accumulator columns 12..15 unused: up to 4 risky (channel, PE)
+// partial sums ride there and the layer keeps the single 16-column set (x2 conv_last: 12 channels, 2 risky pairs).
+static bool spare_column_layout(const LayerConst& c) {
+  if (!(c.pe_exact && c.add_inert && c.epi == EPI_FINAL && c.cout <= 12)) return false;
+  int pairs = 0;
+  for (int co = 0; co < c.cout; ++co) {
+    if (c.pe_risky[co] > 3) return false;
+    if (c.pe_risky[co] >= 0) ++pairs;
+  }
+  return pairs <= 4;
+}
+
 // Accumulator layout for this layer (see header): 1, 2 or 4 sets of 16 columns.
 static int accumulator_sets(const LayerConst& c) {
   if (!c.pe_exact) return 1;
+  if (spare_column_layout(c)) return 1;
   if (!c.add_inert) return 4;                  // the adder-tree clamp can fire: literal tree
   int pairs = 0;
   for (int co = 0; co < c.cout; ++co) {
@@ -1102,6 +1132,12 @@ static void column_role(const LayerConst& c, int ns, bool natural, int n, int* c
     return;
   }
   const int co = natural ? nn : chan_of_byte(nn);
+  if (ns == 1 && nn >= 12 && spare_column_layout(c)) {       // spare column 12 + j carries risky pair j
+    int cols[16], chans[16], pes[16];
+    const int cnt = risky_pairs(c, natural, cols, chans, pes);
+    if (nn - 12 < cnt) { *co_out = chans[nn - 12]; *only_pe = pes[nn - 12]; }
+    return;
+  }
   if (co >= c.cout) return;
   *co_out = co;
   if (ns == 4) *only_pe = set;
@@ -1261,12 +1297,13 @@ static void fill_epilogue_params(UmmaParams& P, const LayerConst& c, int ns) {
       P.c_kmagic[n] = c.add_const[co] + MAGIC_BITS;
     }
   }
-  if (ns == 2) {
+  if (ns == 2 || (ns == 1 && spare_column_layout(c))) {
     int cols[16], chans[16], pes[16];
     P.n_risky = risky_pairs(c, natural, cols, chans, pes);
     for (int j = 0; j < P.n_risky; ++j) {
       P.risky_col[j] = cols[j];
-      P.c_init[1][j] = c.pe_corr[pes[j]][chans[j]];
+      if (ns == 2) P.c_init[1][j] = c.pe_corr[pes[j]][chans[j]];
+      else P.c_init[0][12 + j] = c.pe_corr[pes[j]][chans[j]];          // spare column: plain integer partial sum
     }
   }
   P.lo_acc = c.lo_acc; P.hi_acc = c.hi_acc; P.lo_add = c.lo_add; P.hi_add = c.hi_add;
