@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--calib-frames", type=int, default=256,
+                    help="frames of 80x960 for the calibration timing (BASELINE config 2); 0 = skip")
     ap.add_argument("--outputs", default="both", choices=["both", "y", "q5"],
                     help="what the last layer materialises: fp32 pixel-shuffled y (sim.py:205), int8 q5 (input.5.pt), or both")
     args = ap.parse_args()
@@ -272,6 +274,44 @@ def main():
                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": (q5_h.numel() if want_q5 else 0) + (y_h.numel() * 4 if want_y else 0),
                "ms_per_step": e_ms, "api": "sesrq_net_forward_i8_host (Int8Net.forward_host), pinned host buffers"}
 
+    # ---- calibration (BASELINE config 2): fake-quant forward + running min/max over the rank's shard of the frames,
+    # one all_reduce(MAX); then the KL calibrator's second pass (2048-bin histograms on device), one all_reduce(SUM)
+    # and the on-device threshold search.  Device-timed, max over ranks. ----
+    calib = None
+    if args.calib_frames > 0:
+        from sesr_pytorch_quantize_b200.fq import FakeQuantNet
+        from sesr_pytorch_quantize_b200.calib import MinMaxCalibrator, KLCalibrator, shard_range
+        ch, cw = 80, 960
+        lo, hi = shard_range(args.calib_frames, rank, world)
+        cgen = torch.Generator().manual_seed(1234 + rank)
+        frames = torch.rand(max(hi - lo, 1), cin, ch, cw, generator=cgen).to(dev)[: hi - lo]
+        fq = FakeQuantNet([torch.from_numpy(w) for w in g.wf], [torch.from_numpy(b) for b in g.bf], r,
+                          residual=True, observe_out=(r == 1), device=dev)
+        fq(frames[:1])                                              # warm-up (module load, workspace)
+        fq.reset_observers()
+        barrier()
+        c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        c0.record()
+        mmc = MinMaxCalibrator(fq)
+        mmc.observe(frames)
+        mm_scales, mm_zeros, _, _ = mmc.finish()                    # includes the all_reduce and the D2H of 12 floats
+        c1.record()
+        fq.reset_observers()
+        klc = KLCalibrator(fq)
+        klc.observe_pass1(frames)
+        klc.begin_pass2()
+        klc.observe_pass2(frames)
+        kl_scales, kl_zeros, kl_idx = klc.finish()
+        c2.record()
+        barrier()
+        tc = torch.tensor([c0.elapsed_time(c1), c1.elapsed_time(c2)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        calib = {"frames": args.calib_frames, "shape": [cin, ch, cw], "minmax_s": float(tc[0]) * 1e-3, "kl_s": float(tc[1]) * 1e-3,
+                 "minmax_frames_per_s": args.calib_frames / (float(tc[0]) * 1e-3), "kl_bin_counts": kl_idx,
+                 "collectives": "all_reduce(MAX) over 12 floats; all_reduce(SUM) over int64 [6,2048]" if world > 1 else "none (1 rank)"}
+        fq.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         secs, thr = cpu_reference_time(case, H, W, 1, 2)
@@ -290,7 +330,7 @@ def main():
                        "input": "torch.rand seed 4321+rank, %.0f MB per step > 126 MB L2 (no L2 flush needed)" % (x.numel() * 4 / 1e6),
                        "parallelism": "dp%d frames sharded, no collective" % world},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "calibration": calib,
             "stack": {"alg_bytes_per_lr_px": sum(lbytes), "achieved_gbs": stack_gbs, "frac_of_hbm_peak": stack_gbs / peak,
                       "int8_tops": 2 * total_macs * B * H * W / (ms_step * 1e-3) / 1e12, "us_per_frame": ms_step * 1e3 / B},
             "layers": per_layer,

@@ -108,9 +108,11 @@ size_t sesrq_ws_bytes(const SesrqNet* net, int B, int H, int W);
 int sesrq_net_forward_i8(const SesrqNet* net, const float* d_x, int B, int H, int W,
                          int8_t* d_q5, float* d_y, void* d_ws, size_t ws_bytes, void* stream);
 
-/* Same call with HOST buffers: copies in, runs, copies out and synchronises `stream`.  Pinned host
- * memory makes the copies asynchronous to the host; pageable memory also works.  The workspace and
- * staging buffers are owned by the net (grown on demand; NOT thread-safe on one handle). */
+/* Same call with HOST buffers: copies in, runs, copies out and returns when the results are in host memory.
+ * The batch is cut into chunks that flow through a 3-stage pipeline (H2D / kernels on `stream` / D2H on two
+ * internal copy streams, double-buffered device staging), so with pinned host memory the PCIe transfers in both
+ * directions overlap the kernels; pageable memory also works.  The workspace and staging buffers are owned by the
+ * net (grown on demand; NOT thread-safe on one handle). */
 int sesrq_net_forward_i8_host(SesrqNet* net, const float* h_x, int B, int H, int W,
                               int8_t* h_q5, float* h_y, void* stream);
 
