@@ -87,6 +87,19 @@ def sample_clocks_stop(proc, path):
     return out
 
 
+def emit(line):
+    """Print the ONE JSON line on the real stdout (everything else -- NCCL banners, warnings -- goes to stderr)."""
+    sys.stdout.flush()
+    os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
+# libraries (NCCL prints its version banner on stdout) must not pollute the one-line contract: route fd 1 to stderr
+# until the result is printed
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def cpu_reference_time(case, H, W, frames, reps):
     """Times the CPU restatement of the reference path (oracle/sesr_oracle.c, all host threads) on `frames`
     frames of the workload shape.  Returns (best seconds, threads)."""
@@ -132,7 +145,7 @@ def run_reference(args, case, H, W, r):
                                    "(oracle/sesr_oracle.c, OpenMP); the Python reference cannot travel" % (frames, H, W)},
         "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -335,7 +348,7 @@ def main():
                       "int8_tops": 2 * total_macs * B * H * W / (ms_step * 1e-3) / 1e12, "us_per_frame": ms_step * 1e3 / B},
             "layers": per_layer,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

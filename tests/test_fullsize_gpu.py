@@ -1,0 +1,65 @@
+"""BASELINE.json's full-size configurations on the GPU, bit-exact against the C oracle (oracle/sesr_oracle.c, itself
+pinned to the numpy oracle and through it to the reference), plus size-independent properties at the bench batch:
+frames are independent (any split of the batch gives the same bytes) and the result is deterministic."""
+import numpy as np
+import pytest
+import torch
+
+import c_oracle
+import sesr_oracle as orc
+from conftest import load_golden
+from sesr_pytorch_quantize_b200 import Int8Net, compile_network
+
+pytestmark = pytest.mark.gpu
+
+
+def nets(case):
+    g = load_golden(case)
+    cnet = compile_network([torch.from_numpy(w) for w in g.wf], [torch.from_numpy(b) for b in g.bf], g.scales, g.zeros, g.r)
+    onet = orc.derive_net(g.wf, g.bf, g.scales, g.zeros, g.r)
+    return g, Int8Net(cnet), c_oracle.CNet(onet)
+
+
+@pytest.mark.parametrize("case,B,H,W", [
+    ("x2_fixture", 1, 1080, 1920),          # config 5: SESR x2, 1080p -> 2160p
+    ("x4_fixture", 2, 540, 960),            # config 3: SESR x4, 540x960 -> 2160x3840
+    ("nrdm_fixture", 3, 80, 960),           # config 4: NRDM_3 on 80x960 batches
+    ("x2_fixture", 2, 250, 1004),           # rows not a multiple of the tile height, width not a multiple of the tile width
+])
+def test_full_size_bit_exact_vs_c_oracle(case, B, H, W):
+    g, net, cn = nets(case)
+    gen = torch.Generator().manual_seed(4321)
+    x = torch.rand(B, g.wf[0].shape[1], H, W, generator=gen)
+    q5_ref, y_ref = cn.forward(x.numpy())
+    q5, y = net(x.cuda())
+    assert np.array_equal(q5.cpu().numpy(), q5_ref)
+    assert np.array_equal(y.cpu().numpy(), y_ref)
+
+
+def test_batch_split_invariance_and_determinism_at_bench_size():
+    g, net, _ = nets("x2_fixture")
+    gen = torch.Generator().manual_seed(99)
+    x = torch.rand(6, 3, 1080, 1920, generator=gen).cuda()
+    q_all, y_all = net(x)
+    q_again, y_again = net(x)
+    assert torch.equal(q_all, q_again) and torch.equal(y_all, y_again)
+    for lo, hi in ((0, 1), (1, 4), (4, 6)):
+        q, y = net(x[lo:hi])
+        assert torch.equal(q, q_all[lo:hi]) and torch.equal(y, y_all[lo:hi])
+
+
+def test_host_pipeline_equals_device_call():
+    # the chunked 3-stream host entry point must give the same bytes as the plain device call
+    g, net, _ = nets("x4_fixture")
+    gen = torch.Generator().manual_seed(5)
+    x = torch.rand(7, 1, 270, 480, generator=gen)
+    q_dev, y_dev = net(x.cuda())
+    qs, ys = net.out_shapes(7, 270, 480)
+    q_h = torch.empty(qs, dtype=torch.int8).pin_memory()
+    y_h = torch.empty(ys, dtype=torch.float32).pin_memory()
+    net.forward_host(x.pin_memory(), q_h, y_h)
+    assert torch.equal(q_h, q_dev.cpu()) and torch.equal(y_h, y_dev.cpu())
+    # y only / q5 only
+    y2 = torch.empty(ys, dtype=torch.float32).pin_memory()
+    net.forward_host(x.pin_memory(), None, y2)
+    assert torch.equal(y2, y_dev.cpu())
