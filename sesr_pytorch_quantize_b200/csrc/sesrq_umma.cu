@@ -250,6 +250,34 @@ struct UmmaParams {
   uint32_t xstage_bytes;                 // one fp32 tile buffer: cin planes of (TH + 2 pad) rows x L0_XP floats
 };
 
+// Stores of the final layer for one pixel: COUT int8 codes to the NCHW q5 planes (stride HW bytes) and the
+// de-quantised values to the pixel-shuffled fp32 output (PixelShuffle(RS): channel n -> plane n / RS^2, row offset
+// (n % RS^2) / RS, column offset n % RS; the RS values of one row are contiguous -> one vector store).
+template <int COUT, int RS>
+__device__ __forceinline__ void final_store(const int (&code)[16], const float (&o)[16], int8_t* __restrict__ qb,
+                                            float* __restrict__ yb, const long long HW, const long long plane, const int Wr) {
+  constexpr int R2 = RS * RS;
+  if (qb) {
+    int8_t* p = qb;
+#pragma unroll
+    for (int n = 0; n < COUT; ++n, p += HW) *p = (int8_t)code[n];
+  }
+  if (yb) {
+#pragma unroll
+    for (int c = 0; c < COUT / R2; ++c) {
+      float* pc = yb + c * plane;
+#pragma unroll
+      for (int i = 0; i < RS; ++i) {
+        float* dst = pc + (long long)i * Wr;
+        const int n0 = c * R2 + i * RS;
+        if constexpr (RS == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[n0], o[n0 + 1], o[n0 + 2], o[n0 + 3]);
+        else if constexpr (RS == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[n0], o[n0 + 1]);
+        else *dst = o[n0];
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // epilogue of one output pixel: 16 (x NS) accumulator columns -> codes.  Shared by both kernels.
 // FLOOR: apply max(y, relu_floor) explicitly.  It is only needed for a ReLU layer whose consumer has z > -128:
@@ -267,7 +295,7 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
       if (j >= P.n_risky) break;
       const int v = acc[1][j];
       const int d = clampi(v, P.lo_acc, P.hi_acc) - v;
-      if (d != 0) {
+      if (d != 0) {                                          // rare: the clamp really fired
         const int col = P.risky_col[j];
 #pragma unroll
         for (int n = 0; n < 16; ++n)
@@ -283,10 +311,10 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
         if (j >= P.n_risky) break;
         const int v = acc[0][12 + j];
         const int d = clampi(v, P.lo_acc, P.hi_acc) - v;
-        if (d != 0) {
+        if (d != 0) {                                        // rare: the clamp really fired
           const int col = P.risky_col[j];
 #pragma unroll
-          for (int n = 0; n < 12; ++n)
+          for (int n = 0; n < 16; ++n)
             if (n == col) acc[0][n] += d;
         }
       }
@@ -315,33 +343,40 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
     // q5 = clamp(rint(y + z5)); out = (q5 - z5) * s5 (:585,:594); columns are in natural channel order.
     // rint via the 1.5*2^23 trick: rm = 12582912 + q5 exactly, its low byte is the int8 code.
     constexpr int R2 = RS * RS;
-    const long long HrWr = HW * R2;
-    const int Wr = P.W * RS;
+    int code[16];
     float o[16];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      if (2 * k < P.cout) {
-        float2 t = f2_add(yv[k], P.z_next);
-        t.x = fminf(fmaxf(t.x, -128.f), 127.f);
-        t.y = fminf(fmaxf(t.y, -128.f), 127.f);
-        const float2 rm = f2_add(t, MAGIC_F);
-        if (qb) {
-          qb[(long long)(2 * k) * HW] = (int8_t)__float_as_int(rm.x);
-          if (2 * k + 1 < P.cout) qb[(long long)(2 * k + 1) * HW] = (int8_t)__float_as_int(rm.y);
-        }
-        const float2 ov = f2_mul(f2_add(rm, P.out_off), P.s_out);
-        o[2 * k] = ov.x;
-        o[2 * k + 1] = ov.y;
-      }
+      float2 t = f2_add(yv[k], P.z_next);
+      t.x = fminf(fmaxf(t.x, -128.f), 127.f);
+      t.y = fminf(fmaxf(t.y, -128.f), 127.f);
+      const float2 rm = f2_add(t, MAGIC_F);
+      code[2 * k] = __float_as_int(rm.x);
+      code[2 * k + 1] = __float_as_int(rm.y);
+      const float2 ov = f2_mul(f2_add(rm, P.out_off), P.s_out);
+      o[2 * k] = ov.x;
+      o[2 * k + 1] = ov.y;
     }
-    if (yb) {
+    const long long plane = HW * R2;                       // one pixel-shuffled output plane
+    const int Wr = P.W * RS;
+    // the three networks of the reference: x4 (16 channels, r = 4), x2 (12, r = 2), NRDM (3, r = 1); anything else
+    // takes the generic loop
+    if (RS == 4 && P.cout == 16) final_store<16, RS>(code, o, qb, yb, HW, plane, Wr);
+    else if (RS == 2 && P.cout == 12) final_store<12, RS>(code, o, qb, yb, HW, plane, Wr);
+    else if (RS == 1 && P.cout == 3) final_store<3, RS>(code, o, qb, yb, HW, plane, Wr);
+    else {
 #pragma unroll
-      for (int n0 = 0; n0 < 16; n0 += RS) {
-        if (n0 < P.cout) {
-          float* dst = yb + (long long)(n0 / R2) * HrWr + (long long)((n0 % R2) / RS) * Wr;
-          if constexpr (RS == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[n0], o[n0 + 1], o[n0 + 2], o[n0 + 3]);
-          else if constexpr (RS == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[n0], o[n0 + 1]);
-          else *dst = o[n0];
+      for (int n = 0; n < 16; ++n)
+        if (n < P.cout && qb) qb[(long long)n * HW] = (int8_t)code[n];
+      if (yb) {
+#pragma unroll
+        for (int n0 = 0; n0 < 16; n0 += RS) {
+          if (n0 < P.cout) {
+            float* dst = yb + (long long)(n0 / R2) * plane + (long long)((n0 % R2) / RS) * Wr;
+            if constexpr (RS == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[n0], o[n0 + 1], o[n0 + 2], o[n0 + 3]);
+            else if constexpr (RS == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[n0], o[n0 + 1]);
+            else *dst = o[n0];
+          }
         }
       }
     }
@@ -466,6 +501,14 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
     const int ngrp = tile_groups<RG>(nblk);
     const bool valid = (ox < P.TW) && (gx < P.W);
     const long long pix0 = (long long)b * HW + (long long)y0 * P.W + gx;
+    // final layer: per-tile output bases (row mb adds mb * W bytes / mb * RS * W * RS floats)
+    int8_t* qb_tile = nullptr;
+    float* yb_tile = nullptr;
+    if (EPI == EPI_FINAL) {
+      constexpr int R2 = RS * RS;
+      if (q5) qb_tile = q5 + (long long)b * P.cout * HW + (long long)y0 * P.W + gx;
+      if (y) yb_tile = y + (long long)b * (P.cout / R2) * (HW * R2) + (long long)y0 * RS * (P.W * RS) + (long long)gx * RS;
+    }
     const int first = (int)((wg + NWG - (G0 % NWG)) % NWG);
     for (int j = first; j < ngrp; j += NWG) {
       const uint32_t G = G0 + j;
@@ -500,9 +543,8 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
             float* yb = nullptr;
             int8_t* qb = nullptr;
             if (EPI == EPI_FINAL) {
-              constexpr int R2 = RS * RS;
-              if (y) yb = y + (long long)b * (P.cout / R2) * (HW * R2) + (long long)(y0 + mb) * RS * (P.W * RS) + (long long)gx * RS;
-              if (q5) qb = q5 + (long long)b * P.cout * HW + (long long)(y0 + mb) * P.W + gx;
+              if (yb_tile) yb = yb_tile + (long long)(mb * RS * RS) * P.W;
+              if (qb_tile) qb = qb_tile + mb * P.W;
             }
             epilogue_pixel<NS, EPI, RS, FLOOR>(P, acc[i & 1], sc[i], out + pix, qb, yb, HW, relu_floor);
           }
