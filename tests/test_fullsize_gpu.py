@@ -63,3 +63,26 @@ def test_host_pipeline_equals_device_call():
     y2 = torch.empty(ys, dtype=torch.float32).pin_memory()
     net.forward_host(x.pin_memory(), None, y2)
     assert torch.equal(y2, y_dev.cpu())
+
+
+@pytest.mark.parametrize("case,B,H,W", [("nrdm_fixture", 3, 37, 250), ("x2_fixture", 2, 41, 124), ("x4_fixture", 2, 9, 1000),
+                                        ("nrdm_fixture", 1, 16, 120), ("x2_fixture", 5, 8, 8)])
+def test_no_write_outside_the_output_buffers(case, B, H, W):
+    """compute-sanitizer is not available on the pool: carve q5 / y out of larger canary-filled allocations and check
+    that not a byte outside them changes (odd channel counts, ragged tile edges, short bottom tiles)."""
+    g, net, cn = nets(case)
+    gen = torch.Generator().manual_seed(H * W)
+    x = torch.rand(B, g.wf[0].shape[1], H, W, generator=gen)
+    qs, ys = net.out_shapes(B, H, W)
+    nq, ny = int(np.prod(qs)), int(np.prod(ys))
+    guard = 1 << 16
+    qbuf = torch.full((nq + 2 * guard,), 0x5A, dtype=torch.int8, device="cuda")
+    ybuf = torch.full((ny + 2 * guard,), -777.25, dtype=torch.float32, device="cuda")
+    q5 = qbuf[guard:guard + nq].view(qs)
+    y = ybuf[guard:guard + ny].view(ys)
+    net(x.cuda(), q5=q5, y=y)
+    torch.cuda.synchronize()
+    assert bool((qbuf[:guard] == 0x5A).all()) and bool((qbuf[guard + nq:] == 0x5A).all())
+    assert bool((ybuf[:guard] == -777.25).all()) and bool((ybuf[guard + ny:] == -777.25).all())
+    q5_ref, y_ref = cn.forward(x.numpy())
+    assert np.array_equal(q5.cpu().numpy(), q5_ref) and np.array_equal(y.cpu().numpy(), y_ref)
