@@ -1304,10 +1304,12 @@ static int launch_ns(int ns, const LayerConst& c, const CUtensorMap& tmap, const
 // extra edge rows per band; the accumulator ring (512 / (16 ns) row slots) must hold at least one tile.  Pick the
 // largest nbw <= the preferred one whose tile buffers fit at least twice next to the fixed shared memory.
 struct TilePlan { int TH, tiles_y, stages, nbw; size_t stage_bytes; };
-static TilePlan choose_tiling(int H, int ns, int k, int pad, size_t row_bytes, size_t slack_bytes, size_t per_row_extra,
+static TilePlan choose_tiling(int H, int ns, bool layer0, int pad, size_t row_bytes, size_t slack_bytes, size_t per_row_extra,
                               size_t fixed) {
   const int nslot = TMEM_COLS / (16 * ns);
-  int want = (ns == 1) ? (k == 3 ? 3 : 2) : (ns == 2 ? 2 : 1);
+  // measured (1080p x2, 16 frames): 16-channel layers are fastest with 2 bands (TH = 16: the 32-slot ring then holds two
+  // tiles, 3x3 0.178 vs 0.185 ms with 3 bands), layer 0 with 3 (taller tiles = fewer halo rows to quantise, 0.344 vs 0.394)
+  int want = (ns == 1) ? (layer0 ? 3 : 2) : (ns == 2 ? 2 : 1);
   if (const char* e = getenv("SESRQ_UMMA_NBW")) want = atoi(e);                  // tuning experiments
   want = std::max(1, std::min(want, std::min(3, nslot / TB)));
   const size_t total = 227 * 1024;
@@ -1394,7 +1396,7 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
   P.x_tma = (encode && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && c.in_zero <= 127.f) ? 1 : 0;
   if (getenv("SESRQ_L0_NO_TMA")) P.x_tma = 0;
   const size_t per_row_extra = P.x_tma ? (size_t)2 * c.cin * L0_XP * 4 : (size_t)L0_SP * 4;
-  const TilePlan tp = choose_tiling(H, ns, c.k, pad, (size_t)L0_EP * 16, 8 * 16, per_row_extra, fixed + 256);
+  const TilePlan tp = choose_tiling(H, ns, true, pad, (size_t)L0_EP * 16, 8 * 16, per_row_extra, fixed + 256);
   if (tp.stages < 2) return SESRQ_EUNSUPPORTED;
   P.TH = tp.TH;
   P.tiles_y = tp.tiles_y;
@@ -1446,11 +1448,11 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
 #define SESRQ_L0_NS(KS_, CIN_)                                                                              \
   do {                                                                                                      \
     if (needs_floor(c)) {                                                                                   \
-      if (ns == 1) return launch_l0_one<KS_, 1, CIN_, true, 16>(xmap, P, L, d_x, d_out, grid, smem, st);          \
+      if (ns == 1) return launch_l0_one<KS_, 1, CIN_, true, 12>(xmap, P, L, d_x, d_out, grid, smem, st);          \
       if (ns == 2) return launch_l0_one<KS_, 2, CIN_, true, 16>(xmap, P, L, d_x, d_out, grid, smem, st);          \
       return launch_l0_one<KS_, 4, CIN_, true, 8>(xmap, P, L, d_x, d_out, grid, smem, st);                        \
     }                                                                                                       \
-    if (ns == 1) return launch_l0_one<KS_, 1, CIN_, false, 16>(xmap, P, L, d_x, d_out, grid, smem, st);           \
+    if (ns == 1) return launch_l0_one<KS_, 1, CIN_, false, 12>(xmap, P, L, d_x, d_out, grid, smem, st);           \
     if (ns == 2) return launch_l0_one<KS_, 2, CIN_, false, 16>(xmap, P, L, d_x, d_out, grid, smem, st);           \
     return launch_l0_one<KS_, 4, CIN_, false, 8>(xmap, P, L, d_x, d_out, grid, smem, st);                         \
   } while (0)
@@ -1491,7 +1493,7 @@ int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, c
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // slack: the last row's rightmost K chunk reaches 2*pad + 1 pixels past the row
   // slack: the last row's rightmost K chunk reaches 2*pad + 1 pixels past the row
-  const TilePlan tp = choose_tiling(H, ns, c.k, pad, (size_t)UMMA_M * 16, (size_t)(2 * pad + 1) * 16, 0, fixed);
+  const TilePlan tp = choose_tiling(H, ns, false, pad, (size_t)UMMA_M * 16, (size_t)(2 * pad + 1) * 16, 0, fixed);
   if (tp.stages < 2) return SESRQ_EUNSUPPORTED;
   P.TH = tp.TH;
   P.tiles_y = tp.tiles_y;
