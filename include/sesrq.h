@@ -192,6 +192,13 @@ int sesrq_op_requant_final(const float* d_x, size_t n, int m16, int shift_n, int
 int sesrq_op_conv_int(const float* d_x, int B, int Cin, int H, int W, const float* d_w, int Cout, int k,
                       float* d_out, void* stream);
 
+/* ---- evaluation post-step of test.py:148-170: out = clip(y + nearest_upsample_r(x), 0, 1) (d_x nullable: no add; the
+ *      x2 model adds the upsampled input outside the network) and, with d_gt, *d_sqerr += sum of squared errors of the
+ *      PSNR the script prints: metric 0 plain values, 1 channel 0 * 255 (:165-166), 2 BT.601 luma of rgb_to_yuv
+ *      (:133-136, C must be 3).  d_y / d_gt / d_out: float32 [B,C,Hr,Wr]; d_x: [B,C,Hr/r,Wr/r]. ------------------ */
+int sesrq_op_sr_post(const float* d_y, const float* d_x, const float* d_gt, int B, int C, int Hr, int Wr, int r, int metric,
+                     float* d_out, double* d_sqerr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

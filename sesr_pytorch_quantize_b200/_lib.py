@@ -91,6 +91,7 @@ SIGNATURES = {
     "sesrq_op_requant": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp]),
     "sesrq_op_requant_final": (_i, [_vp, _sz, _i, _i, _i, _d, _vp, _vp, _vp]),
     "sesrq_op_conv_int": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "sesrq_op_sr_post": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

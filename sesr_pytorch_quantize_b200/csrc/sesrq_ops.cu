@@ -142,7 +142,59 @@ __global__ void op_conv_int_kernel(const float* __restrict__ x, int Cin, int H, 
   }
 }
 
+// Evaluation post-step of test.py:148-170 on device: out = clip(y + nearest_upsample(x), 0, 1) (the x2 model adds the
+// upsampled input OUTSIDE the network, :149-155) and the squared-error sum of the PSNR the script prints:
+//   metric 0: plain image values (compare_psnr, data_range 1),  metric 1: channel 0 * 255 (:165-166, x4),
+//   metric 2: BT.601 luma of rgb_to_yuv (:133-136, :167-168, x2), clipped to [0, 255].
+// One thread per HR pixel; fp64 partial sums, one atomicAdd per CTA.
+__global__ void __launch_bounds__(256) sr_post_kernel(const float* __restrict__ y, const float* __restrict__ x,
+                                                      const float* __restrict__ gt, int B, int C, int Hr, int Wr, int r,
+                                                      int metric, float* __restrict__ out, double* __restrict__ sqerr) {
+  const size_t plane = (size_t)Hr * Wr;
+  const size_t n = (size_t)B * plane;
+  double acc = 0.0;
+  EW_LOOP(i, n) {
+    const size_t b = i / plane, p = i - b * plane;
+    const int hy = (int)(p / Wr), wx = (int)(p - (size_t)hy * Wr);
+    const int H = Hr / r, W = Wr / r;
+    double ypred = 0.0, ygt = 0.0;
+    for (int c = 0; c < C; ++c) {
+      const size_t o = (b * C + c) * plane + p;
+      float v = y[o];
+      if (x) v = __fadd_rn(v, x[((b * C + c) * H + hy / r) * (size_t)W + wx / r]);
+      v = fminf(fmaxf(v, 0.f), 1.f);
+      if (out) out[o] = v;
+      if (gt) {
+        const float g = gt[o];
+        if (metric == 0) { const double d = (double)g - (double)v; acc += d * d; }
+        else if (metric == 1) { if (c == 0) { const double d = (double)g * 255.0 - (double)v * 255.0; acc += d * d; } }
+        else {
+          const double wgt = c == 0 ? 65.481 : (c == 1 ? 128.553 : 24.966);
+          ypred += (double)v * wgt;
+          ygt += (double)g * wgt;
+        }
+      }
+    }
+    if (gt && metric == 2) {
+      const double a = fmin(fmax(ygt + 16.0, 0.0), 255.0), bb = fmin(fmax(ypred + 16.0, 0.0), 255.0);
+      acc += (a - bb) * (a - bb);
+    }
+  }
+  if (!gt) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double s_acc[8];
+  if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_acc[w];
+    atomicAdd(sqerr, t);
+  }
+}
+
 }  // namespace sesrq
+
 
 using namespace sesrq;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
@@ -228,6 +280,19 @@ int sesrq_op_conv_int(const float* d_x, int B, int Cin, int H, int W, const floa
   if (n == 0) return SESRQ_OK;
   op_conv_int_kernel<<<ew_grid(n), EW_THREADS, 0, ST(stream)>>>(d_x, Cin, H, W, d_w, Cout, k, n, d_out);
   SESRQ_LAUNCH_CHECK("op_conv_int_kernel");
+  return SESRQ_OK;
+}
+
+int sesrq_op_sr_post(const float* d_y, const float* d_x, const float* d_gt, int B, int C, int Hr, int Wr, int r, int metric,
+                     float* d_out, double* d_sqerr, void* stream) {
+  if (!d_y || B < 0 || C < 1 || Hr < 1 || Wr < 1 || r < 1 || Hr % r || Wr % r || metric < 0 || metric > 2) return SESRQ_EINVAL;
+  if (d_gt && !d_sqerr) return SESRQ_EINVAL;
+  if (metric == 2 && C != 3) return SESRQ_EINVAL;
+  const size_t n = (size_t)B * Hr * Wr;
+  if (n == 0) return SESRQ_OK;
+  sr_post_kernel<<<ew_grid(n), EW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_y, d_x, d_gt, B, C, Hr, Wr, r, metric,
+                                                                                       d_out, d_sqerr);
+  SESRQ_LAUNCH_CHECK("sr_post_kernel");
   return SESRQ_OK;
 }
 

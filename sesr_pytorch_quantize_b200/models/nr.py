@@ -1,0 +1,8 @@
+"""nr.nr: 3 -> 3 channel denoiser, float / fake-quant variant (AddOp residual).  Mirror of the reference's models/nr.py
+(test.py mflag 1); same five-conv topology as nrdm_3, so the fused fake-quant / calibration path applies unchanged."""
+from models._sesr_family import FiveConvNet
+
+
+class nr(FiveConvNet):
+    def __init__(self, in_channels=3, out_channels=3, num_channels=16, num_lblocks=3, scaling_factor=1):
+        super().__init__(in_channels, out_channels, num_channels, num_lblocks, scaling_factor, sim=False, shuffle=False)

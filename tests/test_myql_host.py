@@ -30,9 +30,11 @@ def test_import_surface_matches_reference():
         assert callable(getattr(graph_modify, name))
     for name in ("myMinMaxObserver", "conv_forward_naive", "sesr_forward_sim"):
         assert hasattr(quan_modules, name)
-    from models import sesr_sim, sesr, sesr_arch_sim, sesr_arch, nrdm_3_sim, nrdm_3
+    from models import sesr_sim, sesr, sesr_arch_sim, sesr_arch, nrdm_3_sim, nrdm_3, nr, dm, nrdm_6
+    assert len(nrdm_6.nr().residual_block) == 6
     for mod, cls, cin, cout in ((sesr_sim, "sesr", 1, 16), (sesr, "sesr", 1, 16), (sesr_arch_sim, "sesr", 3, 12),
-                                (sesr_arch, "sesr", 3, 12), (nrdm_3_sim, "nr", 3, 3), (nrdm_3, "nr", 3, 3)):
+                                (sesr_arch, "sesr", 3, 12), (nrdm_3_sim, "nr", 3, 3), (nrdm_3, "nr", 3, 3),
+                                (nr, "nr", 3, 3), (dm, "dm", 3, 3), (nrdm_6, "nr", 3, 3)):
         m = getattr(mod, cls)()
         assert m.conv_first.conv_expand.in_channels == cin
         m.before_quantization()
