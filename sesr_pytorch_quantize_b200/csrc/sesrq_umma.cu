@@ -278,6 +278,24 @@ __device__ __forceinline__ void final_store(const int (&code)[16], const float (
   }
 }
 
+// Final-layer arithmetic for the first NP channel pairs: q5 = clamp(rint(y + z5)); out = (q5 - z5) * s5
+// (quan_func.py:585,:594).  rint via the 1.5*2^23 trick: rm = 12582912 + q5 exactly, its low byte is the int8 code.
+template <int NP>
+__device__ __forceinline__ void final_math(const UmmaParams& P, const float2 (&yv)[8], int (&code)[16], float (&o)[16]) {
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    float2 t = f2_add(yv[k], P.z_next);
+    t.x = fminf(fmaxf(t.x, -128.f), 127.f);
+    t.y = fminf(fmaxf(t.y, -128.f), 127.f);
+    const float2 rm = f2_add(t, MAGIC_F);
+    code[2 * k] = __float_as_int(rm.x);
+    code[2 * k + 1] = __float_as_int(rm.y);
+    const float2 ov = f2_mul(f2_add(rm, P.out_off), P.s_out);
+    o[2 * k] = ov.x;
+    o[2 * k + 1] = ov.y;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // epilogue of one output pixel: 16 (x NS) accumulator columns -> codes.  Shared by both kernels.
 // FLOOR: apply max(y, relu_floor) explicitly.  It is only needed for a ReLU layer whose consumer has z > -128:
@@ -345,26 +363,15 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
     constexpr int R2 = RS * RS;
     int code[16];
     float o[16];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float2 t = f2_add(yv[k], P.z_next);
-      t.x = fminf(fmaxf(t.x, -128.f), 127.f);
-      t.y = fminf(fmaxf(t.y, -128.f), 127.f);
-      const float2 rm = f2_add(t, MAGIC_F);
-      code[2 * k] = __float_as_int(rm.x);
-      code[2 * k + 1] = __float_as_int(rm.y);
-      const float2 ov = f2_mul(f2_add(rm, P.out_off), P.s_out);
-      o[2 * k] = ov.x;
-      o[2 * k + 1] = ov.y;
-    }
     const long long plane = HW * R2;                       // one pixel-shuffled output plane
     const int Wr = P.W * RS;
     // the three networks of the reference: x4 (16 channels, r = 4), x2 (12, r = 2), NRDM (3, r = 1); anything else
     // takes the generic loop
-    if (RS == 4 && P.cout == 16) final_store<16, RS>(code, o, qb, yb, HW, plane, Wr);
-    else if (RS == 2 && P.cout == 12) final_store<12, RS>(code, o, qb, yb, HW, plane, Wr);
-    else if (RS == 1 && P.cout == 3) final_store<3, RS>(code, o, qb, yb, HW, plane, Wr);
+    if (RS == 4 && P.cout == 16) { final_math<8>(P, yv, code, o); final_store<16, RS>(code, o, qb, yb, HW, plane, Wr); }
+    else if (RS == 2 && P.cout == 12) { final_math<6>(P, yv, code, o); final_store<12, RS>(code, o, qb, yb, HW, plane, Wr); }
+    else if (RS == 1 && P.cout == 3) { final_math<2>(P, yv, code, o); final_store<3, RS>(code, o, qb, yb, HW, plane, Wr); }
     else {
+      final_math<8>(P, yv, code, o);
 #pragma unroll
       for (int n = 0; n < 16; ++n)
         if (n < P.cout && qb) qb[(long long)n * HW] = (int8_t)code[n];
