@@ -866,7 +866,7 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   uint64_t* x_empty = x_full + L0_XSTAGES;               // [L0_XSTAGES] count = builder warps
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(x_empty + L0_XSTAGES);
 
-  __shared__ uint32_t stage_w[L0_BUILD_WARPS][4][32];       // builders: one row of pixel words per pass in flight
+  __shared__ uint32_t stage_w[L0_BUILD_WARPS][UMMA_M + 4];   // builders: the pixel words of the tile row in flight
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -954,48 +954,37 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     int st = 0;
     uint32_t ph = 0;
     if (P.x_tma) {
-      // ---- TMA path: every warp pass turns 32 consecutive pixels of one tile row (read from the fp32 tile in shared
-      // memory) into L0_CHUNK operand entries E[row][X] = (w(X), w(X+1), w(X+2), w(X+3)); the neighbours' words come by
-      // warp shuffle, consecutive passes overlap by 3 pixels.  Two passes are computed together on packed pairs. ----
-      constexpr int NCH = (L0_EP + L0_CHUNK - 1) / L0_CHUNK;          // passes per row
+      // ---- TMA path: one warp turns one tile row at a time into operand entries.  The row's 128 pixels (4 passes of 32
+      // lanes, every address = row base + immediate) are quantised on packed pairs and staged as 4-byte words in shared
+      // memory; entry E[row][X] = (w(X), w(X+1), w(X+2), w(X+3)) is then one own word + three staged neighbours (warp
+      // shuffles were measured ~5x slower next to the UMMA traffic).  Words 128..131 only meet zero weights. ----
       const int bwid = bt >> 5;
       const int rp = P.TH + 2 * PAD;                                   // rows per fp32 plane
+      uint32_t* const sw = stage_w[bwid];
+      if (lane < 4) sw[UMMA_M + lane] = 0u;
       int xs = 0;
       uint32_t xph = 0;
       for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
         const int r = t % tiles_per_frame;
-        const int rows = min(P.TH, P.H - (r / P.tiles_x) * P.TH) + 2 * PAD;
+        const int rows = (P.dbg & 256) ? 0 : min(P.TH, P.H - (r / P.tiles_x) * P.TH) + 2 * PAD;
         const int delta = ((r % P.tiles_x) * P.TW - PAD) & 3;          // pixels the aligned box starts early
         if (lane == 0) {
-          if (!(P.dbg & 512)) mbar_wait(&x_full[xs], xph);
+          mbar_wait(&x_full[xs], xph);
           mbar_wait(&e_empty[st], ph ^ 1);                             // the MMAs that read this E stage have retired
         }
         __syncwarp();
-        const float* xsrc = reinterpret_cast<const float*>(region2 + (size_t)xs * P.xstage_bytes);
-        uint4* e = reinterpret_cast<uint4*>(e0 + (size_t)st * P.stage_bytes);
-        const int items = (P.dbg & 256) ? 0 : rows * NCH;
-        // 4 passes per iteration (independent dependency chains: the builders are latency-bound), no lane-divergent
-        // branch anywhere: out-of-range passes / pixels are clamped to valid addresses and only the store is predicated
-        constexpr int UB = 4;
-        for (int it = bwid; it < items; it += UB * L0_BUILD_WARPS) {
-          int eidx[UB];
-          bool ok[UB];
-          float v[UB][CIN];
+        const float* xsrc = reinterpret_cast<const float*>(region2 + (size_t)xs * P.xstage_bytes) + delta + lane;
+        uint4* e = reinterpret_cast<uint4*>(e0 + (size_t)st * P.stage_bytes) + lane;
+        for (int row = bwid; row < rows; row += L0_BUILD_WARPS) {
+          const float* xr = xsrc + row * L0_XP;
+          float v[4][CIN];
 #pragma unroll
-          for (int u = 0; u < UB; ++u) {
-            const int item = it + u * L0_BUILD_WARPS;
-            const int itc = min(item, items - 1);
-            const int row = itc / NCH;
-            const int X = (itc - row * NCH) * L0_CHUNK + lane;
-            ok[u] = item < items && lane < L0_CHUNK && X < L0_EP;
-            eidx[u] = row * L0_EP + X;
-            const int xl = min(X + delta, L0_XP - 1);                  // X >= 132 only feeds "don't care" bytes
+          for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int c = 0; c < CIN; ++c) v[u][c] = xsrc[(c * rp + row) * L0_XP + xl];
-          }
-          uint32_t w0[UB];
+            for (int c = 0; c < CIN; ++c) v[u][c] = xr[c * rp * L0_XP + 32 * u];
+          uint32_t w0[4];
 #pragma unroll
-          for (int u = 0; u < UB; u += 2) {
+          for (int u = 0; u < 4; u += 2) {
             int q[2][4] = {{-128, -128, -128, -128}, {-128, -128, -128, -128}};   // unused channels: byte 0 (zero weights)
 #pragma unroll
             for (int c = 0; c < CIN; ++c) {
@@ -1006,16 +995,14 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
             w0[u] = pack4_sat_s8(q[0][0], q[0][1], q[0][2], q[0][3]) ^ 0x80808080u;
             w0[u + 1] = pack4_sat_s8(q[1][0], q[1][1], q[1][2], q[1][3]) ^ 0x80808080u;
           }
-          // neighbours' words through a per-warp staging row in shared memory (warp shuffles were measured ~5x slower
-          // here: 0.27 ms of a 0.60 ms kernel)
 #pragma unroll
-          for (int u = 0; u < UB; ++u) stage_w[bwid][u][lane] = w0[u];
+          for (int u = 0; u < 4; ++u) sw[32 * u + lane] = w0[u];
           __syncwarp();
+          uint4* er = e + row * L0_EP;
 #pragma unroll
-          for (int u = 0; u < UB; ++u) {
-            const uint32_t* sw = stage_w[bwid][u];
-            const uint32_t w1 = sw[min(lane + 1, 31)], w2 = sw[min(lane + 2, 31)], w3 = sw[min(lane + 3, 31)];
-            if (ok[u]) e[eidx[u]] = make_uint4(w0[u], w1, w2, w3);
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t* s1 = sw + 32 * u + lane + 1;
+            er[32 * u] = make_uint4(w0[u], s1[0], s1[1], s1[2]);
           }
           __syncwarp();
         }
