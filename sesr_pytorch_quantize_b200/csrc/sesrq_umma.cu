@@ -296,6 +296,32 @@ __device__ __forceinline__ void final_math(const UmmaParams& P, const float2 (&y
   }
 }
 
+// Final layer of the x2 network (12 channels, r = 2), math and stores interleaved pair by pair: the packed result of
+// channels (2k, 2k+1) IS the float2 that PixelShuffle(2) places at output row i = k & 1 of plane k >> 1, so it is stored
+// straight from its register pair (no staging arrays, no register moves).
+template <bool Q, bool Y>
+__device__ __forceinline__ void final_x2(const UmmaParams& P, const float2 (&yv)[8], int8_t* __restrict__ qb,
+                                         float* __restrict__ yb, const long long HW, const long long plane, const int Wr) {
+  int8_t* qp = qb;
+  float* yp = yb;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    float2 t = f2_add(yv[k], P.z_next);
+    t.x = fminf(fmaxf(t.x, -128.f), 127.f);
+    t.y = fminf(fmaxf(t.y, -128.f), 127.f);
+    const float2 rm = f2_add(t, MAGIC_F);
+    if (Q) {
+      qp[0] = (int8_t)__float_as_int(rm.x);
+      qp[HW] = (int8_t)__float_as_int(rm.y);
+      qp += 2 * HW;
+    }
+    if (Y) {
+      *reinterpret_cast<float2*>(yp) = f2_mul(f2_add(rm, P.out_off), P.s_out);
+      yp += (k & 1) ? plane - Wr : Wr;                       // row 0 -> row 1 of the plane -> row 0 of the next plane
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // epilogue of one output pixel: 16 (x NS) accumulator columns -> codes.  Shared by both kernels.
 // FLOOR: apply max(y, relu_floor) explicitly.  It is only needed for a ReLU layer whose consumer has z > -128:
@@ -328,8 +354,8 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
       for (int j = 0; j < 4; ++j) {
         if (j >= P.n_risky) break;
         const int v = acc[0][12 + j];
-        const int d = clampi(v, P.lo_acc, P.hi_acc) - v;
-        if (d != 0) {                                        // rare: the clamp really fired
+        if ((unsigned)(v - P.lo_acc) > (unsigned)(P.hi_acc - P.lo_acc)) {   // rare: the clamp really fires
+          const int d = clampi(v, P.lo_acc, P.hi_acc) - v;
           const int col = P.risky_col[j];
 #pragma unroll
           for (int n = 0; n < 16; ++n)
@@ -368,7 +394,11 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
     // the three networks of the reference: x4 (16 channels, r = 4), x2 (12, r = 2), NRDM (3, r = 1); anything else
     // takes the generic loop
     if (RS == 4 && P.cout == 16) { final_math<8>(P, yv, code, o); final_store<16, RS>(code, o, qb, yb, HW, plane, Wr); }
-    else if (RS == 2 && P.cout == 12) { final_math<6>(P, yv, code, o); final_store<12, RS>(code, o, qb, yb, HW, plane, Wr); }
+    else if (RS == 2 && P.cout == 12) {
+      if (qb && yb) final_x2<true, true>(P, yv, qb, yb, HW, plane, Wr);
+      else if (yb) final_x2<false, true>(P, yv, qb, yb, HW, plane, Wr);
+      else final_x2<true, false>(P, yv, qb, yb, HW, plane, Wr);
+    }
     else if (RS == 1 && P.cout == 3) { final_math<2>(P, yv, code, o); final_store<3, RS>(code, o, qb, yb, HW, plane, Wr); }
     else {
       final_math<8>(P, yv, code, o);
@@ -533,6 +563,9 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
       int acc[2][NS][16];
       uint32_t slot = ring.base + (uint32_t)mb0;
       slot_load<NS>(tq + slot * NCOLS, acc[0]);
+      // final layer: output pointers of the group's first row (row i adds i * W bytes / i * RS^2 * W floats)
+      int8_t* const qb_grp = (EPI == EPI_FINAL) ? qb_tile + mb0 * P.W : nullptr;
+      float* const yb_grp = (EPI == EPI_FINAL) ? yb_tile + (long long)(mb0 * RS * RS) * P.W : nullptr;
 #pragma unroll
       for (int i = 0; i < RG; ++i) {
         if (i < cnt) {                     // warp-uniform
@@ -550,8 +583,10 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
             float* yb = nullptr;
             int8_t* qb = nullptr;
             if (EPI == EPI_FINAL) {
-              if (yb_tile) yb = yb_tile + (long long)(mb * RS * RS) * P.W;
-              if (qb_tile) qb = qb_tile + mb * P.W;
+              yb = yb_grp + (long long)(i * RS * RS) * P.W;          // null stays null-ish only if yb_tile was null:
+              qb = qb_grp + i * P.W;                                //   guarded below
+              if (!yb_tile) yb = nullptr;
+              if (!qb_tile) qb = nullptr;
             }
             epilogue_pixel<NS, EPI, RS, FLOOR>(P, acc[i & 1], sc[i], out + pix, qb, yb, HW, relu_floor);
           }
