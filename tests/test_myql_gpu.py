@@ -133,3 +133,29 @@ def test_observer_module_on_device():
     ob(b.cuda())
     assert float(ob.min_val) == float(torch.minimum(a.min(), b.min()))
     assert float(ob.max_val) == float(torch.maximum(a.max(), b.max()))
+
+
+def test_quan_modules_debug_helpers(fresh_state):
+    """conv_forward_naive (step-wise 18-bit clamp, reference quan_modules.py:43-99) and sesr_forward_sim (:101-201): the
+    reference's hand-unrolled debugging path.  Without clamp events it must agree with the fused network (for the x4 model
+    the final ReLU of sesr_forward_sim is a no-op because z5 = -128)."""
+    import torch.nn.functional as F
+    from myQL.quan_modules import conv_forward_naive, sesr_forward_sim
+    from myQL.quan_func import quantize_model_weight
+    import define
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randint(0, 255, (1, 3, 9, 11), generator=gen).float().cuda()
+    w = torch.randint(-20, 20, (4, 3, 3, 3), generator=gen).float().cuda()
+    assert torch.equal(conv_forward_naive(x, w, 1, 1, 0), F.conv2d(x, w, padding=1))
+    big = torch.full((1, 1, 3, 3), 255.0).cuda()
+    wbig = torch.full((1, 1, 3, 3), 127.0).cuda()
+    assert float(conv_forward_naive(big, wbig, 1, 1, 0).max()) == 2 ** 17 - 1          # 9 * 255 * 127 saturates at 18 bits
+
+    g = load_golden("x4_small")
+    set_thresholds(fresh_state, g)
+    model = collapsed_model(g, sim=True, device="cuda")
+    quantize_model_weight(model, define.QUAN_BIT, 1)                                    # fills state.weight_codes / scales
+    for i, b in enumerate(g.bf):
+        fresh_state.bias[i] = torch.from_numpy(b)
+    y = sesr_forward_sim(torch.from_numpy(g.x).cuda())
+    assert np.array_equal(y.cpu().numpy(), g["yout"])
