@@ -201,6 +201,13 @@ def main():
     qs, ys = net.out_shapes(B, H, W)
     want_q5, want_y = args.outputs in ("both", "q5"), args.outputs in ("both", "y")
     q5 = torch.empty(qs, dtype=torch.int8, device=dev) if want_q5 else None
+    if want_q5 and os.environ.get("SESRQ_BENCH_Q5_OFFSET"):      # address-aliasing experiments: shift the q5 base
+        off = int(os.environ["SESRQ_BENCH_Q5_OFFSET"])
+        n = 1
+        for d in qs:
+            n *= d
+        _q5_backing = torch.empty(n + off + 4096, dtype=torch.int8, device=dev)
+        q5 = _q5_backing[off:off + n].view(qs)
     y = torch.empty(ys, dtype=torch.float32, device=dev) if want_y else None
 
     def barrier():

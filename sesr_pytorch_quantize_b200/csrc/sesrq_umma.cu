@@ -327,7 +327,9 @@ __device__ __forceinline__ void final_x2(const UmmaParams& P, const float2 (&yv)
 // FLOOR: apply max(y, relu_floor) explicitly.  It is only needed for a ReLU layer whose consumer has z > -128:
 // with z <= -128, clamp(rint(max(y,0) + z)) == clamp(rint(y + z)) because every y < 0 saturates at -128 either way.
 // ------------------------------------------------------------------------------------------------
-template <int NS, int EPI, int RS, bool FLOOR>
+// OUTM (final layer): 0 = both outputs may be wanted, decided by the pointers at run time; 1 = q5 only, 2 = y only
+// (compile time: the single-output kernels carry only their own store sequence, which makes them markedly faster).
+template <int NS, int EPI, int RS, int OUTM, bool FLOOR>
 __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[NS][16], const uint4 sc,
                                                uint4* __restrict__ out_px, int8_t* __restrict__ qb,
                                                float* __restrict__ yb, const long long HW, const float relu_floor) {
@@ -395,7 +397,9 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
     // takes the generic loop
     if (RS == 4 && P.cout == 16) { final_math<8>(P, yv, code, o); final_store<16, RS>(code, o, qb, yb, HW, plane, Wr); }
     else if (RS == 2 && P.cout == 12) {
-      if (qb && yb) final_x2<true, true>(P, yv, qb, yb, HW, plane, Wr);
+      if (OUTM == 2) final_x2<false, true>(P, yv, qb, yb, HW, plane, Wr);
+      else if (OUTM == 1) final_x2<true, false>(P, yv, qb, yb, HW, plane, Wr);
+      else if (qb && yb) final_x2<true, true>(P, yv, qb, yb, HW, plane, Wr);
       else if (yb) final_x2<false, true>(P, yv, qb, yb, HW, plane, Wr);
       else final_x2<true, false>(P, yv, qb, yb, HW, plane, Wr);
     }
@@ -496,7 +500,7 @@ __device__ __forceinline__ void slot_fence(int (&a)[NS][16]) {
   }
 }
 
-template <int NS, int EPI, int RS, bool FLOOR, int EPI_WARPS>
+template <int NS, int EPI, int RS, int OUTM, bool FLOOR, int EPI_WARPS>
 __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ewarp, const int lane, const uint32_t tmem_base,
                                                uint64_t* acc_full, uint64_t* acc_empty,
                                                const uint4* __restrict__ shortcut, uint4* __restrict__ out,
@@ -543,8 +547,8 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
     float* yb_tile = nullptr;
     if (EPI == EPI_FINAL) {
       constexpr int R2 = RS * RS;
-      if (q5) qb_tile = q5 + (long long)b * P.cout * HW + (long long)y0 * P.W + gx;
-      if (y) yb_tile = y + (long long)b * (P.cout / R2) * (HW * R2) + (long long)y0 * RS * (P.W * RS) + (long long)gx * RS;
+      if (q5 && OUTM != 2) qb_tile = q5 + (long long)b * P.cout * HW + (long long)y0 * P.W + gx;
+      if (y && OUTM != 1) yb_tile = y + (long long)b * (P.cout / R2) * (HW * R2) + (long long)y0 * RS * (P.W * RS) + (long long)gx * RS;
     }
     const int first = (int)((wg + NWG - (G0 % NWG)) % NWG);
     for (int j = first; j < ngrp; j += NWG) {
@@ -585,10 +589,10 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
             if (EPI == EPI_FINAL) {
               yb = yb_grp + (long long)(i * RS * RS) * P.W;          // null stays null-ish only if yb_tile was null:
               qb = qb_grp + i * P.W;                                //   guarded below
-              if (!yb_tile) yb = nullptr;
-              if (!qb_tile) qb = nullptr;
+              if (!yb_tile || OUTM == 1) yb = nullptr;
+              if (!qb_tile || OUTM == 2) qb = nullptr;
             }
-            epilogue_pixel<NS, EPI, RS, FLOOR>(P, acc[i & 1], sc[i], out + pix, qb, yb, HW, relu_floor);
+            epilogue_pixel<NS, EPI, RS, OUTM, FLOOR>(P, acc[i & 1], sc[i], out + pix, qb, yb, HW, relu_floor);
           }
           tmem_st_wait();                  // warp-collective: every lane's re-arm store has landed
           tc_fence_before();
@@ -727,7 +731,7 @@ __device__ __forceinline__ void mma_issue_band(const int bw, const int lane, con
 // the kernel.  KS: kernel size; NS: accumulator sets (1/2/4, see header); EPI: EpilogueKind; RS: PixelShuffle
 // factor of the final epilogue (1 otherwise); EPI_WARPS: number of epilogue warps.
 // ------------------------------------------------------------------------------------------------
-template <int KS, int NS, int EPI, int RS, bool FLOOR, int EPI_WARPS>
+template <int KS, int NS, int EPI, int RS, int OUTM, bool FLOOR, int EPI_WARPS>
 __global__ void __launch_bounds__((CTRL_WARPS + EPI_WARPS) * 32, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ UmmaParams P,
                  const uint8_t* __restrict__ w_img, const uint4* __restrict__ shortcut, uint4* __restrict__ out,
@@ -817,7 +821,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     }
   } else {
     // ================= epilogue =================
-    epilogue_warps<NS, EPI, RS, FLOOR, EPI_WARPS>(P, warp - CTRL_WARPS, lane, tmem_base, acc_full, acc_empty, shortcut, out, q5, y);
+    epilogue_warps<NS, EPI, RS, OUTM, FLOOR, EPI_WARPS>(P, warp - CTRL_WARPS, lane, tmem_base, acc_full, acc_empty, shortcut, out,
+                                                        q5, y);
   }
 
   // ---- teardown ----
@@ -978,7 +983,7 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     }
   } else if (warp < CTRL_WARPS + EPI_WARPS) {
     // ================= epilogue (shared with the 16-channel kernel, EPI_PLAIN) =================
-    epilogue_warps<NS, EPI_PLAIN, 1, FLOOR, EPI_WARPS>(P, warp - CTRL_WARPS, lane, tmem_base, acc_full, acc_empty, nullptr, out,
+    epilogue_warps<NS, EPI_PLAIN, 1, 0, FLOOR, EPI_WARPS>(P, warp - CTRL_WARPS, lane, tmem_base, acc_full, acc_empty, nullptr, out,
                                                        nullptr, nullptr);
   } else {
     // ================= builders =================
@@ -1284,10 +1289,10 @@ int umma_prepare_layer(LayerDev& L, const int8_t* w) {
   return umma_upload(L, img, "umma weight upload");
 }
 
-template <int KS, int NS, int EPI, int RS, bool FLOOR, int EPI_WARPS>
+template <int KS, int NS, int EPI, int RS, int OUTM, bool FLOOR, int EPI_WARPS>
 static int launch_one(const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L, const uint8_t* d_shortcut,
                       uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem, cudaStream_t st) {
-  auto kern = conv_umma_kernel<KS, NS, EPI, RS, FLOOR, EPI_WARPS>;
+  auto kern = conv_umma_kernel<KS, NS, EPI, RS, OUTM, FLOOR, EPI_WARPS>;
   static bool attr_set = false;
   if (!attr_set) {
     SESRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1303,16 +1308,24 @@ template <int KS, int NS, int EPI_WARPS>
 static int launch_epi(const LayerConst& c, const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L,
                       const uint8_t* d_shortcut, uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem,
                       cudaStream_t st) {
-#define SESRQ_GO(EPI_, RS_, FLOOR_) \
-  return launch_one<KS, NS, EPI_, RS_, FLOOR_, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st)
+#define SESRQ_GO(EPI_, RS_, OUTM_, FLOOR_) \
+  return launch_one<KS, NS, EPI_, RS_, OUTM_, FLOOR_, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st)
+#define SESRQ_GO_FINAL(RS_)                              \
+  do {                                                   \
+    if (d_q5 && d_y) SESRQ_GO(EPI_FINAL, RS_, 0, false); \
+    if (d_y) SESRQ_GO(EPI_FINAL, RS_, 2, false);         \
+    SESRQ_GO(EPI_FINAL, RS_, 1, false);                  \
+  } while (0)
   if (c.epi == EPI_PLAIN) {
-    if (needs_floor(c)) SESRQ_GO(EPI_PLAIN, 1, true);
-    SESRQ_GO(EPI_PLAIN, 1, false);
+    if (needs_floor(c)) SESRQ_GO(EPI_PLAIN, 1, 0, true);
+    SESRQ_GO(EPI_PLAIN, 1, 0, false);
   }
-  if (c.epi == EPI_RESIDUAL) SESRQ_GO(EPI_RESIDUAL, 1, false);
-  if (c.r_shuffle == 4) SESRQ_GO(EPI_FINAL, 4, false);
-  if (c.r_shuffle == 2) SESRQ_GO(EPI_FINAL, 2, false);
-  SESRQ_GO(EPI_FINAL, 1, false);
+  if (c.epi == EPI_RESIDUAL) SESRQ_GO(EPI_RESIDUAL, 1, 0, false);
+  if (!d_q5 && !d_y) return SESRQ_EINVAL;
+  if (c.r_shuffle == 4) SESRQ_GO_FINAL(4);
+  if (c.r_shuffle == 2) SESRQ_GO_FINAL(2);
+  SESRQ_GO_FINAL(1);
+#undef SESRQ_GO_FINAL
 #undef SESRQ_GO
 }
 
