@@ -263,10 +263,11 @@ def main():
                           "achieved_gbs": gbs, "share": layer_ms[i] / max(sum(layer_ms), 1e-9)})
     dom = max(range(5), key=lambda i: layer_ms[i])
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("layer%d" % dom)
-    except (OSError, ValueError):
-        pass
+    if args.outputs == "both" and not args.batch:          # the ncu capture was taken on the default configuration
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("layer%d" % dom)
+        except (OSError, ValueError):
+            pass
     roofline = {"bound": "hbm", "kernel": "layer %d (%s)" % (dom, per_layer[dom]["impl"]),
                 "achieved": per_layer[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": per_layer[dom]["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src}

@@ -123,3 +123,37 @@ def test_input_quantiser_rounding_boundaries(case, impl):
     q5, y = net(torch.from_numpy(x).cuda())
     assert np.array_equal(q5.cpu().numpy(), q5_ref)
     assert np.array_equal(y.cpu().numpy(), y_ref)
+
+
+@pytest.mark.parametrize("impl", impl_ids())
+@pytest.mark.parametrize("case,shape", [
+    ("x2_fixture", (2, 130, 257)), ("x4_fixture", (2, 67, 301)), ("nrdm_fixture", (2, 33, 129)),
+    ("x2_fixture", (1, 40, 512)), ("synth_clamp", (1, 40, 150)),
+])
+def test_single_output_calls_match_both(case, shape, impl):
+    """The last layer has separate kernels for "q5 only" and "y only"; each must give what the two-output call gives
+    and leave the other buffer alone (canary)."""
+    g = load_golden(case)
+    B, H, W = shape
+    cin = g.wf[0].shape[1]
+    gen = torch.Generator().manual_seed(77 + H * W)
+    x = torch.rand(B, cin, H, W, generator=gen)
+    if int(g["signed_input"]):
+        x = x * 2 - 1
+    x = x.cuda()
+    net = build(g, impl)
+    q5_both, y_both = net(x)
+    q5_both, y_both = q5_both.clone(), y_both.clone()
+    q5_only, none_y = net(x, want_q5=True, want_y=False)
+    assert none_y is None
+    assert torch.equal(q5_only, q5_both)
+    none_q, y_only = net(x, want_q5=False, want_y=True)
+    assert none_q is None
+    assert torch.equal(y_only, y_both)
+    # caller-provided buffers: the unwanted one is not written
+    q5_buf = torch.full_like(q5_both, 77)
+    y_buf = torch.full_like(y_both, -5.0)
+    net(x, want_q5=False, want_y=True, y=y_buf)
+    assert torch.equal(y_buf, y_both)
+    net(x, want_q5=True, want_y=False, q5=q5_buf)
+    assert torch.equal(q5_buf, q5_both)
