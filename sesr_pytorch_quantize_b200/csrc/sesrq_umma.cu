@@ -1346,12 +1346,11 @@ static int launch_ns(int ns, const LayerConst& c, const CUtensorMap& tmap, const
 // extra edge rows per band; the accumulator ring (512 / (16 ns) row slots) must hold at least one tile.  Pick the
 // largest nbw <= the preferred one whose tile buffers fit at least twice next to the fixed shared memory.
 struct TilePlan { int TH, tiles_y, stages, nbw; size_t stage_bytes; };
-static TilePlan choose_tiling(int H, int ns, bool layer0, int pad, size_t row_bytes, size_t slack_bytes, size_t per_row_extra,
+static TilePlan choose_tiling(int H, int ns, int prefer, int pad, size_t row_bytes, size_t slack_bytes, size_t per_row_extra,
                               size_t fixed) {
   const int nslot = TMEM_COLS / (16 * ns);
-  // measured (1080p x2, 16 frames): 16-channel layers are fastest with 2 bands (TH = 16: the 32-slot ring then holds two
-  // tiles, 3x3 0.178 vs 0.185 ms with 3 bands), layer 0 with 3 (taller tiles = fewer halo rows to quantise, 0.344 vs 0.394)
-  int want = (ns == 1) ? (layer0 ? 3 : 2) : (ns == 2 ? 2 : 1);
+  // `prefer` = the caller's measured band count for NS = 1 (see launch_conv_umma / launch_conv_umma_l0)
+  int want = (ns == 1) ? prefer : (ns == 2 ? 2 : 1);
   if (const char* e = getenv("SESRQ_UMMA_NBW")) want = atoi(e);                  // tuning experiments
   want = std::max(1, std::min(want, std::min(3, nslot / TB)));
   const size_t total = 227 * 1024;
@@ -1438,7 +1437,14 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
   P.x_tma = (encode && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && c.in_zero <= 127.f) ? 1 : 0;
   if (getenv("SESRQ_L0_NO_TMA")) P.x_tma = 0;
   const size_t per_row_extra = P.x_tma ? (size_t)2 * c.cin * L0_XP * 4 : (size_t)L0_SP * 4;
-  const TilePlan tp = choose_tiling(H, ns, true, pad, (size_t)L0_EP * 16, 8 * 16, per_row_extra, fixed + 256);
+  // Bands of 8 rows per tile, 2 or 3: the cost is (rows incl. the padding of the last tile) x (cost per row), and per
+  // row 3 bands are ~5 % cheaper for RGB input (fewer halo rows to quantise: 1080p x2 0.278 vs 0.292 ms) but ~4 % dearer
+  // for single-channel input (x4 540x960: 0.271 vs 0.256 ms); the padding decides for short frames (H = 80: 96 vs 80
+  // rows, 0.197 vs 0.178 ms).
+  const double rows2 = (double)cdiv(H, 2 * TB) * 2 * TB, rows3 = (double)cdiv(H, 3 * TB) * 3 * TB;
+  int prefer = (c.cin == 1 ? rows3 * 1.04 < rows2 : rows3 * 0.95 <= rows2) ? 3 : 2;
+  if (const char* e = getenv("SESRQ_UMMA_NBW_L0")) prefer = atoi(e);            // tuning experiments
+  const TilePlan tp = choose_tiling(H, ns, prefer, pad, (size_t)L0_EP * 16, 8 * 16, per_row_extra, fixed + 256);
   if (tp.stages < 2) return SESRQ_EUNSUPPORTED;
   P.TH = tp.TH;
   P.tiles_y = tp.tiles_y;
@@ -1535,7 +1541,12 @@ int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, c
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // slack: the last row's rightmost K chunk reaches 2*pad + 1 pixels past the row
   // slack: the last row's rightmost K chunk reaches 2*pad + 1 pixels past the row
-  const TilePlan tp = choose_tiling(H, ns, false, pad, (size_t)UMMA_M * 16, (size_t)(2 * pad + 1) * 16, 0, fixed);
+  // measured: 16-channel layers are fastest with 2 bands (TH = 16: the 32-slot ring then holds two tiles; 1080p x2 3x3
+  // 0.178 vs 0.185 ms with 3 bands); the 16-output x4 final layer with 3 (540x960: 0.909 vs 0.955 ms)
+  int prefer = (c.epi == EPI_FINAL && c.r_shuffle == 4) ? 3 : 2;
+  if (c.epi == EPI_FINAL)
+    if (const char* e = getenv("SESRQ_UMMA_NBW_FINAL")) prefer = atoi(e);       // tuning experiments
+  const TilePlan tp = choose_tiling(H, ns, prefer, pad, (size_t)UMMA_M * 16, (size_t)(2 * pad + 1) * 16, 0, fixed);
   if (tp.stages < 2) return SESRQ_EUNSUPPORTED;
   P.TH = tp.TH;
   P.tiles_y = tp.tiles_y;
