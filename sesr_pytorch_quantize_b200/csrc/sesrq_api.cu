@@ -309,6 +309,7 @@ int sesrq_net_forward_i8(const SesrqNet* net, const float* d_x, int B, int H, in
   if (!net || B < 0 || H <= 0 || W <= 0) return SESRQ_EINVAL;
   if (B == 0) return SESRQ_OK;
   if (!d_x || !d_ws) return SESRQ_EINVAL;
+  if (!d_q5 && !d_y) return SESRQ_EINVAL;                       // nothing to materialise
   if ((long long)H * W > (1LL << 30)) return SESRQ_EINVAL;
   WsPlan p = plan_ws(net, B, H, W);
   if (ws_bytes < p.total) return SESRQ_ENOMEM;
@@ -395,7 +396,7 @@ int sesrq_net_forward_i8_host(SesrqNet* net, const float* h_x, int B, int H, int
                               float* h_y, void* stream) {
   if (!net || B < 0 || H <= 0 || W <= 0) return SESRQ_EINVAL;
   if (B == 0) return SESRQ_OK;
-  if (!h_x) return SESRQ_EINVAL;
+  if (!h_x || (!h_q5 && !h_y)) return SESRQ_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t hw = (size_t)H * W;
   const int cin = net->layers[0].c.cin, cout = net->layers[4].c.cout;

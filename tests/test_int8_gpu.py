@@ -157,3 +157,11 @@ def test_single_output_calls_match_both(case, shape, impl):
     assert torch.equal(y_buf, y_both)
     net(x, want_q5=True, want_y=False, q5=q5_buf)
     assert torch.equal(q5_buf, q5_both)
+
+
+def test_call_without_any_output_is_rejected():
+    g = load_golden("x2_small")
+    net = build(g, IMPL_AUTO)
+    x = torch.from_numpy(g.x).cuda()
+    with pytest.raises(SesrqError):
+        net(x, want_q5=False, want_y=False)
