@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--calib-frames", type=int, default=256,
                     help="frames of 80x960 for the calibration timing (BASELINE config 2); 0 = skip")
+    ap.add_argument("--no-variants", action="store_true", help="skip the y-only / q5-only timings of the default run")
     ap.add_argument("--outputs", default="both", choices=["both", "y", "q5"],
                     help="what the last layer materialises: fp32 pixel-shuffled y (sim.py:205), int8 q5 (input.5.pt), or both")
     args = ap.parse_args()
@@ -333,6 +334,26 @@ def main():
                  "collectives": "all_reduce(MAX) over 12 floats; all_reduce(SUM) over int64 [6,2048]" if world > 1 else "none (1 rank)"}
         fq.close()
 
+    # ---- the same step when the caller wants one output only (model(inps) of the reference needs only y) ----
+    single = None
+    if args.outputs == "both" and world == 1 and not args.no_variants:
+        single = {}
+        for name, wq, wy in (("y_only", False, True), ("q5_only", True, False)):
+            for _ in range(3):
+                net(x, want_q5=wq, want_y=wy, q5=q5, y=y)
+            torch.cuda.synchronize(dev)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(args.steps):
+                net(x, want_q5=wq, want_y=wy, q5=q5, y=y)
+            s1.record()
+            torch.cuda.synchronize(dev)
+            ms = s0.elapsed_time(s1) / args.steps
+            nbytes = sum(layer_bytes_per_px(cin, cout, wq, wy))
+            single[name] = {"value": B * out_px_frame / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": ms,
+                            "alg_bytes_per_lr_px": nbytes,
+                            "frac_of_hbm_peak": nbytes * B * H * W / (ms * 1e-3) / 1e9 / peak}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         secs, thr = cpu_reference_time(case, H, W, 1, 2)
@@ -351,7 +372,7 @@ def main():
                        "input": "torch.rand seed 4321+rank, %.0f MB per step > 126 MB L2 (no L2 flush needed)" % (x.numel() * 4 / 1e6),
                        "parallelism": "dp%d frames sharded, no collective" % world},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "calibration": calib,
+            "cpu_baseline": cpu, "calibration": calib, "single_output": single,
             "stack": {"alg_bytes_per_lr_px": sum(lbytes), "achieved_gbs": stack_gbs, "frac_of_hbm_peak": stack_gbs / peak,
                       "int8_tops": 2 * total_macs * B * H * W / (ms_step * 1e-3) / 1e12, "us_per_frame": ms_step * 1e3 / B},
             "layers": per_layer,
