@@ -38,3 +38,16 @@ def test_default_arm_needs_a_gpu():
     p = run_bench("--steps", "1", "--warmup", "1", "--no-cpu", "--no-e2e", "--calib-frames", "0")
     assert p.returncode != 0, "the product arm must fail loudly without a GPU, not fall back"
     assert not [l for l in p.stdout.splitlines() if l.strip().startswith("{")]
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """Launched the way the driver launches N > 1: rank 0 alone runs and prints, the other rank exits 0."""
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
+                        "--workload", "sesr_x2_int8_sim_80x960"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2
