@@ -19,9 +19,8 @@ import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "tests")):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (golden case holding weights + thresholds, H, W, default per-GPU batch)
@@ -42,8 +41,81 @@ def layer_bytes_per_px(cin, cout, want_q5=True, want_y=True):
 
 
 def load_case(name):
-    from conftest import load_golden
+    from sesr_pytorch_quantize_b200.fixtures import load_golden
     return load_golden(name)
+
+
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def workload_config(workload, case, B, H, W, r, cin, cout, outputs, world, input_mb):
+    """The `config` object, shared by the product arm and the reference arm (same keys and values for the same flags)."""
+    return {"workload": workload, "frames_per_gpu_per_step": B, "H": H, "W": W, "upscale": r, "cin": cin, "cout": cout,
+            "outputs": {"both": "q5 int8 NCHW + fp32 pixel-shuffled y", "y": "fp32 pixel-shuffled y (what model(inps) returns, sim.py:205)",
+                        "q5": "q5 int8 NCHW (input.5.pt)"}[outputs],
+            "weights": "reference checkpoint collapsed (tests/golden/%s.npz), reference min/max thresholds" % case,
+            "input": "torch.rand seed 4321+rank, %.0f MB per step > 126 MB L2 (no L2 flush needed)" % input_mb,
+            "parallelism": "dp%d frames sharded, no collective" % world}
+
+
+def bind_to_gpu_numa(torch, index):
+    """Bind this rank to the CPUs local to its GPU (sysfs local_cpulist of the PCI device), so that pinned host buffers
+    are first-touched on the GPU's NUMA node.  Returns a short description for the bench line."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bus
+        node = open(base + "/numa_node").read().strip()
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"pci": bus, "numa_node": int(node), "cpus": len(cpus)}
+    except (OSError, ValueError, AttributeError) as e:
+        return {"unavailable": str(e)[:120]}
+
+
+def copy_ceiling(torch, dev, h2d_bytes, d2h_bytes, reps, barrier):
+    """What the PCIe / host-memory path alone allows for one step's transfers: the step's H2D and D2H volumes as two
+    concurrent pinned copies on two streams, no kernels (all ranks at once).  Returns ms per step."""
+    hi = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    ho = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    di = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    do = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    def once():
+        with torch.cuda.stream(s1):
+            di.copy_(hi, non_blocking=True)
+        with torch.cuda.stream(s2):
+            ho.copy_(do, non_blocking=True)
+    once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / reps
+    barrier()
+    return dt * 1e3
+
+
+def python_reference_time(case, H, W, frames=1, mode=1, timeout=900):
+    """The REAL reference (unmodified Python myQL + models staged in oracle/_ref) timed on this host in a subprocess
+    (oracle/time_ref.py).  Returns the parsed JSON or {"unavailable": why}."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "time_ref.py"), "--case", os.path.join(ROOT, "tests", "golden", case + ".npz"),
+           "--h", str(H), "--w", str(W), "--frames", str(frames), "--mode", str(mode), "--threads", str(host_cores())]
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        if p.returncode != 0 or not lines:
+            return {"unavailable": "oracle/time_ref.py failed: " + (p.stderr.strip().splitlines() or ["?"])[-1][:200]}
+        return json.loads(lines[-1])
+    except (OSError, subprocess.TimeoutExpired, ValueError) as e:
+        return {"unavailable": str(e)[:200]}
 
 
 def sample_clocks_start(gpu_index):
@@ -110,6 +182,7 @@ def cpu_reference_time(case, H, W, frames, reps):
     g = load_case(case)
     onet = orc.derive_net(g.wf, g.bf, g.scales, g.zeros, g.r)
     cn = c_oracle.CNet(onet)
+    c_oracle.set_threads(host_cores())           # explicit: torchrun exports OMP_NUM_THREADS=1
     x = np.random.default_rng(4321).random((frames, g.wf[0].shape[1], H, W), dtype=np.float32)
     best = None
     for _ in range(reps):
@@ -120,14 +193,18 @@ def cpu_reference_time(case, H, W, frames, reps):
     return best, c_oracle.threads()
 
 
-def run_reference(args, case, H, W, r):
+def run_reference(args, case, H, W, r, B, cin, cout):
+    """`--impl reference`: the reference path on this box's host cores with the product arm's config (same frames per
+    step).  Primary number = the C restatement (oracle/sesr_oracle.c, all host threads: it is 17-27x faster than the
+    Python reference, so ratios against it are conservative); the real Python reference (oracle/_ref) is timed on one
+    frame beside it and reported in `python_reference`.  Under torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     out_px = H * W * r * r
-    frames = 1
+    frames = B
     for _ in range(max(args.warmup, 0)):
-        cpu_reference_time(case, H, W, frames, 1)
+        cpu_reference_time(case, H, W, min(frames, 2), 1)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_reference_time(case, H, W, frames, 1)
@@ -135,14 +212,23 @@ def run_reference(args, case, H, W, r):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle
     val = frames * out_px / dt / 1e6
+    pyref = None
+    if not args.no_python_ref:
+        pr = python_reference_time(case, H, W, frames=1, mode=1)
+        pyref = pr if "unavailable" in pr else {
+            "value": out_px / pr["s_per_frame_best"] / 1e6, "unit": "Mpix/s", "cores": pr["threads"], "kind": "reference",
+            "s_per_frame": pr["s_per_frame_best"],
+            "sample": "1 frame of %dx%d through the unmodified myQL + models (sim.py:82-114,205 path, dumps off), staged in oracle/%s" % (H, W, pr["reference_root"])}
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "H": H, "W": W, "frames_per_step": frames},
+        "config": workload_config(args.workload, case, B, H, W, r, cin, cout, args.outputs, max(args.gpus, 1),
+                                  B * cin * H * W * 4 / 1e6),
         "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": c_oracle.threads(), "kind": "port",
                          "sample": "%d frame(s) of %dx%d per step, C restatement of the reference path "
-                                   "(oracle/sesr_oracle.c, OpenMP); the Python reference cannot travel" % (frames, H, W)},
+                                   "(oracle/sesr_oracle.c, OpenMP, %d threads set explicitly)" % (frames, H, W, c_oracle.threads())},
+        "python_reference": pyref,
         "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -163,8 +249,11 @@ def main():
     ap.add_argument("--calib-frames", type=int, default=256,
                     help="frames of 80x960 for the calibration timing (BASELINE config 2); 0 = skip")
     ap.add_argument("--no-variants", action="store_true", help="skip the y-only / q5-only timings of the default run")
-    ap.add_argument("--outputs", default="both", choices=["both", "y", "q5"],
-                    help="what the last layer materialises: fp32 pixel-shuffled y (sim.py:205), int8 q5 (input.5.pt), or both")
+    ap.add_argument("--outputs", default="y", choices=["both", "y", "q5"],
+                    help="what the last layer materialises: fp32 pixel-shuffled y (what model(inps) returns, sim.py:205; default), "
+                         "int8 q5 (input.5.pt, written upstream only with INPUT_W_FLG), or both")
+    ap.add_argument("--no-python-ref", action="store_true", help="skip timing the real Python reference (oracle/_ref)")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the other BASELINE shapes / batch sweep")
     args = ap.parse_args()
     case, H, W, defB = WORKLOADS[args.workload]
     B = args.batch or defB
@@ -174,7 +263,7 @@ def main():
     out_px_frame = H * W * r * r
 
     if args.impl == "reference":
-        run_reference(args, case, H, W, r)
+        run_reference(args, case, H, W, r, B, cin, cout)
         return
 
     import torch
@@ -188,6 +277,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the sesrq hot path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa(torch, local)          # before the pinned buffers are allocated (first touch)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = load_library()
@@ -264,9 +354,9 @@ def main():
                           "achieved_gbs": gbs, "share": layer_ms[i] / max(sum(layer_ms), 1e-9)})
     dom = max(range(5), key=lambda i: layer_ms[i])
     traffic = None
-    if args.outputs == "both" and not args.batch:          # the ncu capture was taken on the default configuration
+    if not args.batch:                                     # the ncu capture was taken on the default batch
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("layer%d" % dom)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload + ":" + args.outputs, {}).get("layer%d" % dom)
         except (OSError, ValueError):
             pass
     roofline = {"bound": "hbm", "kernel": "layer %d (%s)" % (dom, per_layer[dom]["impl"]),
@@ -292,9 +382,19 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e_ms = float(te.item()) / args.e2e_steps
+        h2d_b = x_host.numel() * 4
+        d2h_b = (q5_h.numel() if want_q5 else 0) + (y_h.numel() * 4 if want_y else 0)
+        tcp = torch.tensor([copy_ceiling(torch, dev, h2d_b, d2h_b, args.e2e_steps, barrier)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tcp, op=dist.ReduceOp.MAX)
+        ceil_ms = float(tcp.item())
         e2e = {"value": world * B * out_px_frame / (e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
-               "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": (q5_h.numel() if want_q5 else 0) + (y_h.numel() * 4 if want_y else 0),
-               "ms_per_step": e_ms, "api": "sesrq_net_forward_i8_host (Int8Net.forward_host), pinned host buffers"}
+               "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+               "ms_per_step": e_ms, "api": "sesrq_net_forward_i8_host (Int8Net.forward_host), pinned host buffers",
+               "copy_ceiling": {"ms_per_step": ceil_ms, "value": world * B * out_px_frame / (ceil_ms * 1e-3) / 1e6,
+                                "gbs_per_rank": (h2d_b + d2h_b) / (ceil_ms * 1e-3) / 1e9,
+                                "what": "the same H2D + D2H volumes as two concurrent pinned copies, no kernels, all %d rank(s) at once" % world},
+               "frac_of_copy_ceiling": ceil_ms / e_ms, "affinity": affinity}
 
     # ---- calibration (BASELINE config 2): fake-quant forward + running min/max over the rank's shard of the frames,
     # one all_reduce(MAX); then the KL calibrator's second pass (2048-bin histograms on device), one all_reduce(SUM)
@@ -305,8 +405,10 @@ def main():
         from sesr_pytorch_quantize_b200.calib import MinMaxCalibrator, KLCalibrator, shard_range
         ch, cw = 80, 960
         lo, hi = shard_range(args.calib_frames, rank, world)
-        cgen = torch.Generator().manual_seed(1234 + rank)
-        frames = torch.rand(max(hi - lo, 1), cin, ch, cw, generator=cgen).to(dev)[: hi - lo]
+        # ONE global calibration set (seed 1234, the goldens' recipe), every rank takes its contiguous shard: the merged
+        # statistics -- and so the thresholds -- are the same for every world size
+        cgen = torch.Generator().manual_seed(1234)
+        frames = torch.rand(args.calib_frames, cin, ch, cw, generator=cgen)[lo:hi].to(dev)
         fq = FakeQuantNet([torch.from_numpy(w) for w in g.wf], [torch.from_numpy(b) for b in g.bf], r,
                           residual=True, observe_out=(r == 1), device=dev)
         fq(frames[:1])                                              # warm-up (module load, workspace)
@@ -329,50 +431,99 @@ def main():
         tc = torch.tensor([c0.elapsed_time(c1), c1.elapsed_time(c2)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        import hashlib
+        thr_hash = hashlib.sha256(repr(([float(v) for v in mm_scales], [int(v) for v in mm_zeros])).encode()).hexdigest()[:16]
         calib = {"frames": args.calib_frames, "shape": [cin, ch, cw], "minmax_s": float(tc[0]) * 1e-3, "kl_s": float(tc[1]) * 1e-3,
                  "minmax_frames_per_s": args.calib_frames / (float(tc[0]) * 1e-3), "kl_bin_counts": kl_idx,
+                 "minmax_threshold_hash": thr_hash, "minmax_zeros": [int(v) for v in mm_zeros],
+                 "frame_set": "global: torch.rand seed 1234, %d frames, contiguous shards" % args.calib_frames,
                  "collectives": "all_reduce(MAX) over 12 floats; all_reduce(SUM) over int64 [6,2048]" if world > 1 else "none (1 rank)"}
         fq.close()
 
-    # ---- the same step when the caller wants one output only (model(inps) of the reference needs only y) ----
+    # ---- the same step for the other output selections (y = what model(inps) returns; q5 = input.5.pt, SURVEY 8d's
+    # base figure of 168 B/px for x2; both = 216 B/px) ----
+    def time_net(net_, x_, wq, wy, q5_, y_, steps):
+        for _ in range(3):
+            net_(x_, want_q5=wq, want_y=wy, q5=q5_, y=y_)
+        torch.cuda.synchronize(dev)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(steps):
+            net_(x_, want_q5=wq, want_y=wy, q5=q5_, y=y_)
+        s1.record()
+        torch.cuda.synchronize(dev)
+        return s0.elapsed_time(s1) / steps
+
     single = None
-    if args.outputs == "both" and world == 1 and not args.no_variants:
+    if world == 1 and not args.no_variants:
         single = {}
-        for name, wq, wy in (("y_only", False, True), ("q5_only", True, False)):
-            for _ in range(3):
-                net(x, want_q5=wq, want_y=wy, q5=q5, y=y)
-            torch.cuda.synchronize(dev)
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            for _ in range(args.steps):
-                net(x, want_q5=wq, want_y=wy, q5=q5, y=y)
-            s1.record()
-            torch.cuda.synchronize(dev)
-            ms = s0.elapsed_time(s1) / args.steps
+        q5v = q5 if q5 is not None else torch.empty(qs, dtype=torch.int8, device=dev)
+        yv = y if y is not None else torch.empty(ys, dtype=torch.float32, device=dev)
+        for name, wq, wy in (("y_only", False, True), ("q5_only", True, False), ("both", True, True)):
+            ms = time_net(net, x, wq, wy, q5v, yv, args.steps)
             nbytes = sum(layer_bytes_per_px(cin, cout, wq, wy))
             single[name] = {"value": B * out_px_frame / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": ms,
                             "alg_bytes_per_lr_px": nbytes,
                             "frac_of_hbm_peak": nbytes * B * H * W / (ms * 1e-3) / 1e9 / peak}
+        del q5v, yv
+
+    # ---- the other BASELINE.json shapes and the batch sweep of config 5, device-timed like `value` (same outputs) ----
+    workloads = None
+    if world == 1 and not args.no_workloads and not args.batch and args.workload == "sesr_x2_int8_sim_1080p":
+        workloads = []
+        del x, q5, y
+        torch.cuda.empty_cache()
+        plan = [(wl, WORKLOADS[wl][3]) for wl in ("sesr_x4_int8_sim_540x960", "nrdm3_int8_sim_80x960", "sesr_x2_int8_sim_80x960",
+                                                  "sesr_x4_int8_sim_80x960")]
+        plan += [("sesr_x2_int8_sim_1080p", b) for b in (1, 8, 64, 512)] + [("sesr_x2_int8_sim_80x960", 1), ("nrdm3_int8_sim_80x960", 1),
+                                                                             ("nrdm3_int8_sim_80x960", 64)]
+        for wl, wb in plan:
+            wcase, wH, wW, _ = WORKLOADS[wl]
+            wg = load_case(wcase)
+            wcin, wcout, wr = wg.wf[0].shape[1], wg.wf[4].shape[0], wg.r
+            need = wb * wH * wW * (4 * wcin + (wcout if want_q5 else 0) + (4 * wcout if want_y else 0) + 64) * 1.1
+            free_b, _tot = torch.cuda.mem_get_info(dev)
+            if need > free_b:
+                workloads.append({"workload": wl, "frames_per_step": wb, "skipped": "needs %.0f GB" % (need / 1e9)})
+                continue
+            wnet = Int8Net(compile_network([torch.from_numpy(w) for w in wg.wf], [torch.from_numpy(b) for b in wg.bf],
+                                           wg.scales, wg.zeros, wr), device=dev)
+            wx = torch.rand(wb, wcin, wH, wW, generator=torch.Generator().manual_seed(4321)).to(dev) if wb * wH * wW * wcin < 5e8 \
+                else torch.rand(wb, wcin, wH, wW, device=dev)
+            wqs, wys = wnet.out_shapes(wb, wH, wW)
+            wq5 = torch.empty(wqs, dtype=torch.int8, device=dev) if want_q5 else None
+            wy_ = torch.empty(wys, dtype=torch.float32, device=dev) if want_y else None
+            ms = time_net(wnet, wx, want_q5, want_y, wq5, wy_, max(3, min(args.steps, 10)))
+            nbytes = sum(layer_bytes_per_px(wcin, wcout, want_q5, want_y))
+            workloads.append({"workload": wl, "frames_per_step": wb, "H": wH, "W": wW, "ms_per_step": ms, "us_per_frame": ms * 1e3 / wb,
+                              "value": wb * wH * wW * wr * wr / (ms * 1e-3) / 1e6, "unit": "Mpix/s (output)",
+                              "alg_bytes_per_lr_px": nbytes, "frac_of_hbm_peak": nbytes * wb * wH * wW / (ms * 1e-3) / 1e9 / peak,
+                              "input_mb": wx.numel() * 4 / 1e6})
+            wnet.close()
+            del wx, wq5, wy_, wnet
+            torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         secs, thr = cpu_reference_time(case, H, W, 1, 2)
         cpu = {"value": out_px_frame / secs / 1e6, "unit": "Mpix/s", "cores": thr, "kind": "port",
-               "sample": "1 frame of %dx%d (best of 2), C restatement of the reference path with OpenMP" % (H, W),
+               "sample": "1 frame of %dx%d (best of 2), C restatement of the reference path with OpenMP (%d threads set explicitly)" % (H, W, thr),
                "s_per_frame": secs}
+        if not args.no_python_ref:
+            pr = python_reference_time(case, H, W, frames=1, mode=1)
+            cpu["python_reference"] = pr if "unavailable" in pr else {
+                "value": out_px_frame / pr["s_per_frame_best"] / 1e6, "unit": "Mpix/s", "cores": pr["threads"], "kind": "reference",
+                "s_per_frame": pr["s_per_frame_best"],
+                "sample": "1 frame of %dx%d through the unmodified myQL + models (sim.py path, dumps off) from oracle/%s" % (H, W, pr["reference_root"])}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.workload, "frames_per_gpu_per_step": B, "H": H, "W": W, "upscale": r,
-                       "cin": cin, "cout": cout, "outputs": {"both": "q5 int8 NCHW + fp32 pixel-shuffled y", "y": "fp32 pixel-shuffled y", "q5": "q5 int8 NCHW"}[args.outputs],
-                       "weights": "reference checkpoint collapsed (tests/golden/%s.npz), reference min/max thresholds" % case,
-                       "input": "torch.rand seed 4321+rank, %.0f MB per step > 126 MB L2 (no L2 flush needed)" % (x.numel() * 4 / 1e6),
-                       "parallelism": "dp%d frames sharded, no collective" % world},
+            "config": workload_config(args.workload, case, B, H, W, r, cin, cout, args.outputs, world, B * cin * H * W * 4 / 1e6),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "calibration": calib, "single_output": single,
+            "cpu_baseline": cpu, "calibration": calib, "output_variants": single, "workloads": workloads,
             "stack": {"alg_bytes_per_lr_px": sum(lbytes), "achieved_gbs": stack_gbs, "frac_of_hbm_peak": stack_gbs / peak,
                       "int8_tops": 2 * total_macs * B * H * W / (ms_step * 1e-3) / 1e12, "us_per_frame": ms_step * 1e3 / B},
             "layers": per_layer,

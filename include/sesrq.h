@@ -171,7 +171,7 @@ int sesrq_fq_forward(const SesrqFq* fq, const float* d_x, int H, int W, float* d
                      const float* d_hist_range, void* d_ws, size_t ws_bytes, void* stream);
 
 /* ---- stand-alone myQL ops on float32 NCHW device tensors (exe_mode 1), for graphs that are not
- *      fused: each replaces one reference callable -------------------------------------------------- */
+ *      fused (partial passes, dump flags set): each replaces one reference callable -------------------------------------------------- */
 /* quantize_asymmetrical_by_tensor, func_id 0 (:222-225) and 1..3 (:275-280): returns q - max(z,-128) */
 int sesrq_op_quant_first(const float* d_x, size_t n, double scale, int zero, float* d_q, float* d_u, void* stream);
 int sesrq_op_quant_next(const float* d_x, size_t n, int zero, float* d_q, float* d_u, void* stream);
@@ -194,12 +194,56 @@ int sesrq_op_requant_final(const float* d_x, size_t n, int m16, int shift_n, int
 int sesrq_op_conv_int(const float* d_x, int B, int Cin, int H, int W, const float* d_w, int Cout, int k,
                       float* d_out, void* stream);
 
+/* ---- the same callables in exe_mode 0 (fake-quant "staged" float, the un-fused test.py graph) ---------------------- */
+/* quantize_asymmetrical_by_tensor exe_mode 0 (:207-215): y = (clamp(rint(x / s + z)) - z) * s; the caller derives
+ * (s, z) from this tensor's min/max (sesrq_minmax_update) as quan_func.py:198-205 does. */
+int sesrq_op_fakequant(const float* d_x, size_t n, double scale, int zero, float* d_y, void* stream);
+/* the nn.Conv2d node of the mode-0 graph: d_x holds (q - z) * s (PE-split), d_wcodes the integer weight codes as
+ * float32 [Cout,Cin,k,k]; exact integer accumulation scaled once by f32(s) * f32(s_w) (bit-identical to sesrq_fq_forward) */
+int sesrq_op_conv_fq(const float* d_x, int B, int Cin, int H, int W, const float* d_wcodes, int Cout, int k,
+                     double in_scale, double w_scale, float* d_out, void* stream);
+/* reshape_ouput_for_hardware_pe + PEs_and_bias_adder exe_mode 0 (:330-333, :386, :431-434, :459) on the PE-split conv
+ * output [4B,Cout,H,W]: clamp each PE to [lo_acc, hi_acc], sum, clamp to [lo_add, hi_add], + d_bias[Cout] (nullable). */
+int sesrq_op_pe_merge_fq(const float* d_conv, int B, int Cout, int HW, float lo_acc, float hi_acc, float lo_add,
+                         float hi_add, const float* d_bias, float* d_out, void* stream);
+
+/* ---- QAT library (models/quantize_utils_cuda.py:150-246 Round + Quantizer.forward): fake-quant forward and the
+ *      straight-through backward.  d_scale / d_zp / d_lo / d_hi hold `rows` entries: 1 (per tensor, q_level "L") or the
+ *      channel count (q_level "C": element i belongs to row (i / inner) % rows).
+ *      fwd: y = (clamp(round_half_away(x / s - zp), qmin, qmax) + zp) * s
+ *      bwd: g_x = (g * s) / s where the clamp and the Round mask (t = x / s - zp inside [lo, hi]) pass, else 0 ------- */
+int sesrq_qat_fakequant_fwd(const float* d_x, size_t n, size_t inner, int rows, const float* d_scale, const float* d_zp,
+                            float qmin, float qmax, float* d_y, void* stream);
+int sesrq_qat_fakequant_bwd(const float* d_x, const float* d_gy, size_t n, size_t inner, int rows, const float* d_scale,
+                            const float* d_zp, const float* d_obs_min, const float* d_obs_max, int q_type, float qmin,
+                            float qmax, float* d_gx, void* stream);
+/* Quantizer.update_qparams (:299-327): q_type 0 symmetric (scale = max(|min|,|max|) / ((qmax - qmin) / 2), zp = 0),
+ * 1 asymmetric (scale = (max - min) / (qmax - qmin), zp = sign(min) * floor(|min / scale| + 0.5)); scale >= eps */
+int sesrq_qat_qparams(const float* d_min, const float* d_max, int rows, int q_type, float qmin, float qmax, float eps,
+                      float* d_scale, float* d_zp, void* stream);
+/* ObserverBase.forward + update_range (:22-35, :68-80, :107-119): (min, max) of each of the `rows` rows of the
+ * [rows, cols] view of d_x, folded into d_min / d_max: mode 0 = set, 1 = running min / max, 2 = moving average
+ * (1 - momentum) * old + momentum * cur.  d_tmp: 2 * rows floats of scratch. */
+int sesrq_qat_observe(const float* d_x, int rows, size_t cols, int mode, float momentum, float* d_min, float* d_max,
+                      float* d_tmp, void* stream);
+/* per-row (min, max) of a [rows, cols] matrix: ObserverBase.forward q_level "C" (:27-30) */
+int sesrq_minmax_rows(const float* d_x, int rows, size_t cols, float* d_min, float* d_max, void* stream);
+/* k-th smallest |x| (1-based; torch.kthvalue(input.abs().view(-1), k) of HistogramObserver, :136-138), exact two-level
+ * radix select on the bit pattern.  d_ws: (65536 + 32768 + 2) * 4 bytes of scratch. */
+int sesrq_kth_abs(const float* d_x, size_t n, unsigned long long k, float* d_out, void* d_ws, size_t ws_bytes, void* stream);
+
 /* ---- evaluation post-step of test.py:148-170: out = clip(y + nearest_upsample_r(x), 0, 1) (d_x nullable: no add; the
  *      x2 model adds the upsampled input outside the network) and, with d_gt, *d_sqerr += sum of squared errors of the
  *      PSNR the script prints: metric 0 plain values, 1 channel 0 * 255 (:165-166), 2 BT.601 luma of rgb_to_yuv
  *      (:133-136, C must be 3).  d_y / d_gt / d_out: float32 [B,C,Hr,Wr]; d_x: [B,C,Hr/r,Wr/r]. ------------------ */
 int sesrq_op_sr_post(const float* d_y, const float* d_x, const float* d_gt, int B, int C, int Hr, int Wr, int r, int metric,
                      float* d_out, double* d_sqerr, void* stream);
+
+/* SSIM of test.py:172-175 (skimage.metrics.structural_similarity with its defaults: 7 x 7 uniform window, K1 = 0.01,
+ * K2 = 0.03, sample covariance; channel_axis = 2 averages the per-plane values): *d_sum += sum of the SSIM map over the
+ * interior (H - 6) x (W - 6) window centres of `planes` planes [planes, H, W]; the caller divides by
+ * planes * (H - 6) * (W - 6). */
+int sesrq_op_ssim(const float* d_a, const float* d_b, int planes, int H, int W, double data_range, double* d_sum, void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,17 @@ def lib():
         _lib.sesr_oracle_forward.argtypes = [C.POINTER(_Net), C.c_void_p, C.c_int, C.c_int, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.sesr_oracle_threads.restype = C.c_int
+        _lib.sesr_oracle_set_threads.argtypes = [C.c_int]
+        _lib.sesr_oracle_set_threads.restype = None
     return _lib
+
+
+def set_threads(n=None):
+    """Use `n` OpenMP threads (default: every core of this process's affinity mask), whatever OMP_NUM_THREADS says."""
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().sesr_oracle_set_threads(int(n))
+    return threads()
 
 
 def threads():

@@ -28,3 +28,28 @@ def psnr(img_hwc, gt_hwc, mflag):
         return compute_psnr(rgb_to_yuv(gt_hwc), rgb_to_yuv(img_hwc))
     mse = np.mean((gt_hwc.astype(np.float64) - img_hwc.astype(np.float64)) ** 2)        # skimage compare_psnr, data_range 1
     return 10. * np.log10(1.0 / mse)
+
+
+def ssim(a, b, data_range=1.0, win_size=7):
+    """skimage.metrics.structural_similarity restated (skimage 0.19+ `_structural_similarity.py`: uniform filter of
+    win_size, K1 = 0.01, K2 = 0.03, use_sample_covariance=True, mean over the map cropped by (win_size - 1) // 2).
+    a, b: [planes, H, W] or [H, W]; planes are averaged like channel_axis.  skimage itself is not installed in this
+    image (parity unpinned against the third-party code; the formula is its published one), scipy's uniform_filter is."""
+    from scipy.ndimage import uniform_filter
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.ndim == 2:
+        a, b = a[None], b[None]
+    k1, k2 = 0.01, 0.03
+    npix = win_size ** 2
+    cov_norm = npix / (npix - 1)
+    c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
+    pad = (win_size - 1) // 2
+    vals = []
+    for x, y in zip(a, b):
+        ux, uy = uniform_filter(x, size=win_size), uniform_filter(y, size=win_size)
+        uxx, uyy, uxy = uniform_filter(x * x, size=win_size), uniform_filter(y * y, size=win_size), uniform_filter(x * y, size=win_size)
+        vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+        s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
+        vals.append(s[pad:-pad, pad:-pad].mean())
+    return float(np.mean(vals))

@@ -150,6 +150,16 @@ int sesr_oracle_forward(const OracleNet* net, const float* x, int B, int H, int 
   return 0;
 }
 
+/* Explicit thread count: a launcher's OMP_NUM_THREADS (torchrun exports 1) must not decide how many host cores the
+ * CPU baseline uses; bench.py passes the size of its affinity mask. */
+void sesr_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int sesr_oracle_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -108,13 +108,18 @@ class OracleNet:
 
 def derive_net(weights_f: Sequence[np.ndarray], biases_f: Sequence[np.ndarray],
                scales: Sequence[float], zeros: Sequence[int], r: int,
-               pe_acc_bit: int = PE_ACC_BIT, pe_add_bit: int = PE_ADD_BIT) -> OracleNet:
-    """All host-side constants of SURVEY App. A from collapsed float weights + calibration."""
-    assert len(weights_f) == 5 and len(scales) == 6 and len(zeros) == 6
+               pe_acc_bit: int = PE_ACC_BIT, pe_add_bit: int = PE_ADD_BIT,
+               codes: Optional[Sequence[np.ndarray]] = None, w_scales: Optional[Sequence[float]] = None) -> OracleNet:
+    """All host-side constants of SURVEY App. A from collapsed float weights + calibration.  With `codes` / `w_scales`
+    the weights are taken as already quantised (what a graph holds after quantize_model_weight); weights_f is unused."""
+    assert len(weights_f if codes is None else codes) == 5 and len(scales) == 6 and len(zeros) == 6
     nxt = [1, 2, 3, 1, 5]                      # requant target domain per layer (:525,:601,:556,:579)
     layers = []
     for i in range(5):
-        W, sw = quantize_weight(weights_f[i])
+        if codes is not None:
+            W, sw = np.asarray(codes[i]).astype(np.int8), float(w_scales[i])
+        else:
+            W, sw = quantize_weight(weights_f[i])
         cout, cin, k, _ = W.shape
         s_i = float(scales[i])
         z_i = int(zeros[i])

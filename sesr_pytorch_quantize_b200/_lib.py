@@ -91,6 +91,16 @@ SIGNATURES = {
     "sesrq_op_requant": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp]),
     "sesrq_op_requant_final": (_i, [_vp, _sz, _i, _i, _i, _d, _vp, _vp, _vp]),
     "sesrq_op_conv_int": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "sesrq_op_fakequant": (_i, [_vp, _sz, _d, _i, _vp, _vp]),
+    "sesrq_op_conv_fq": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _d, _d, _vp, _vp]),
+    "sesrq_op_pe_merge_fq": (_i, [_vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp]),
+    "sesrq_qat_fakequant_fwd": (_i, [_vp, _sz, _sz, _i, _vp, _vp, _f, _f, _vp, _vp]),
+    "sesrq_qat_fakequant_bwd": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp, _vp, _vp, _i, _f, _f, _vp, _vp]),
+    "sesrq_qat_qparams": (_i, [_vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp]),
+    "sesrq_qat_observe": (_i, [_vp, _i, _sz, _i, _f, _vp, _vp, _vp, _vp]),
+    "sesrq_kth_abs": (_i, [_vp, _sz, C.c_ulonglong, _vp, _vp, _sz, _vp]),
+    "sesrq_minmax_rows": (_i, [_vp, _i, _sz, _vp, _vp, _vp]),
+    "sesrq_op_ssim": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp]),
     "sesrq_op_sr_post": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 

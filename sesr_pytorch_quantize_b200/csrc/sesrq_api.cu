@@ -61,7 +61,8 @@ struct SesrqNet {
   bool need_rc = false;       // z_1 != -128: shortcut codes differ from q_1 (quan_func.py:250 vs :280)
   bool need_a0 = false;       // layer 0 runs on the generic path -> separate input-quantise pass
   int device = 0;
-  size_t chunk_bytes = (size_t)2048 << 20;   // activation workspace per pass (SESRQ_CHUNK_MB)
+  size_t chunk_bytes = (size_t)2048 << 20;   // activation workspace per pass (SESRQ_CHUNK_MB, read at create)
+  int host_chunk = 0;                        // frames per host-pipeline chunk (SESRQ_HOST_CHUNK, read at create; 0 = auto)
   // host-call staging (sesrq_net_forward_i8_host): two sets of device buffers, copy-in / copy-out streams
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
@@ -179,6 +180,7 @@ int sesrq_net_create(const SesrqNetDesc* d, SesrqNet** out_net) {
     long v = atol(e);
     if (v > 0) net->chunk_bytes = (size_t)v << 20;
   }
+  if (const char* e = getenv("SESRQ_HOST_CHUNK")) net->host_chunk = std::max(0, atoi(e));
   int zs[SESRQ_NUM_DOMAINS];
   for (int i = 0; i < SESRQ_NUM_LAYERS; ++i) zs[i] = d->layers[i].z_in;
   zs[5] = d->z_out;
@@ -212,6 +214,7 @@ int sesrq_net_create(const SesrqNetDesc* d, SesrqNet** out_net) {
     c.relu = l.relu;
     c.save_rc = (i == 0 && net->need_rc) ? 1 : 0;
     c.r_shuffle = d->r_shuffle;
+    c.first_layer = (i == 0) ? 1 : 0;
     c.mf = (float)((double)l.m16 * std::ldexp(1.0, -l.shift_n));               // exact: m16 < 2^16
     // layer 3 requantises into domain 1 (:554-560) but its codes are consumed by the residual
     // quantiser of layer 4, which adds z_4 (:270); z_next is unused by EPI_RESIDUAL.
@@ -409,12 +412,15 @@ int sesrq_net_forward_i8_host(SesrqNet* net, const float* h_x, int B, int H, int
   // 1 frame/chunk 54.5 ms, 2: 38.5, 4: 39.4, 8: 40.2, unpipelined 45.1; the D2H volume alone is 36 ms at 55 GB/s)
   int chunk = (int)std::max<size_t>((B + 7) / 8, (((size_t)32 << 20) + frame_io - 1) / std::max<size_t>(frame_io, 1));
   chunk = std::min(std::max(chunk, 2), B);
-  if (const char* e = getenv("SESRQ_HOST_CHUNK")) chunk = std::max(1, std::min(B, atoi(e)));   // tuning experiments
+  if (net->host_chunk > 0) chunk = std::min(B, net->host_chunk);             // tuning experiments
   const int nchunks = (B + chunk - 1) / chunk;
   const size_t x_bytes = up((size_t)chunk * cin * hw * 4);
   const size_t q_bytes = h_q5 ? up((size_t)chunk * cout * hw) : 0;
   const size_t y_bytes = h_y ? up((size_t)chunk * cout * hw * 4) : 0;
-  const size_t ws_bytes = sesrq_ws_bytes(net, chunk, H, W);
+  // the workspace plan balances frames over passes, so it is not monotonic in the frame count: size it for the
+  // full chunks AND for the tail chunk
+  const int tail = B % chunk;
+  const size_t ws_bytes = std::max(sesrq_ws_bytes(net, chunk, H, W), tail ? sesrq_ws_bytes(net, tail, H, W) : (size_t)0);
   const size_t set_bytes = x_bytes + q_bytes + y_bytes;
   const size_t need = 2 * set_bytes + ws_bytes;
   if (need > net->stage_bytes) {
@@ -454,7 +460,13 @@ int sesrq_net_forward_i8_host(SesrqNet* net, const float* h_x, int B, int H, int
     SESRQ_CUDA(cudaStreamWaitEvent(st, net->ev_in[s], 0));
     if (k >= 2) SESRQ_CUDA(cudaStreamWaitEvent(st, net->ev_out[s], 0));      // output buffers s drained by chunk k-2's D2H
     int rc = sesrq_net_forward_i8(net, d_x, nf, H, W, d_q5, d_y, d_ws, ws_bytes, stream);
-    if (rc) return rc;
+    if (rc) {
+      // copies to / from the caller's buffers may still be in flight: drain them before handing control back
+      cudaStreamSynchronize(net->s_in);
+      cudaStreamSynchronize(net->s_out);
+      cudaStreamSynchronize(st);
+      return rc;
+    }
     SESRQ_CUDA(cudaEventRecord(net->ev_comp[s], st));
     SESRQ_CUDA(cudaStreamWaitEvent(net->s_out, net->ev_comp[s], 0));
     if (h_q5)

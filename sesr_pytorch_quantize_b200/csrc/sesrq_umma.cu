@@ -32,6 +32,7 @@
 // All three issue the same number of MMAs; the tensor pipe has the headroom.
 #include <cuda.h>
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -220,6 +221,38 @@ __device__ __forceinline__ int tile_groups(int nblk) {         // groups of a ti
   return (nblk / TB) * (TB / RG) + ((nblk % TB) + RG - 1) / RG;
 }
 
+// experiment switches for the final-layer epilogue (tools/variants.sh builds one library per combination)
+#ifdef SESRQ_X_NOPIPE
+constexpr bool X_NOPIPE = true;      // no software pipelining of the TMEM loads (one accumulator buffer)
+#else
+constexpr bool X_NOPIPE = false;
+#endif
+#ifdef SESRQ_X_BRANCH
+constexpr bool X_BRANCH = true;      // out-of-frame lanes branch around the row instead of predicating every store
+#else
+constexpr bool X_BRANCH = false;
+#endif
+#ifdef SESRQ_X_ROWARRIVE
+constexpr bool X_ROWARRIVE = true;   // re-arm completion signalled per row (RG arrivals per warp and group) instead of once per group
+#else
+constexpr bool X_ROWARRIVE = false;
+#endif
+// The 4 warps of a warpgroup meet at a named barrier before every row, so that their stores to the same output rows
+// (q5: 4 x 32 misaligned bytes of one plane row = whole sectors only together; y: 4 x 256 B of one HR row) leave the SM
+// within a few hundred cycles of each other.  Measured on 16 x 1080p: final layer both 0.745 -> 0.626 ms, y only
+// 0.435 -> 0.411 (profiles/r2_final_layer.txt); 0 = off, 1 = final layer (default), 2 = every layer.
+#ifndef SESRQ_X_ROWSYNC
+#define SESRQ_X_ROWSYNC 1
+#endif
+#ifndef SESRQ_X_STCS
+#define SESRQ_X_STCS 0               // 1: streaming (evict-first) stores for y, 2: for y and q5
+#endif
+#ifdef SESRQ_X_NOPIN
+constexpr bool X_NOPIN = true;
+#else
+constexpr bool X_NOPIN = false;
+#endif
+
 constexpr int32_t MAGIC_BITS = 0x4B400000;
 constexpr float MAGIC_F = 12582912.f;
 
@@ -250,19 +283,30 @@ struct UmmaParams {
   uint32_t xstage_bytes;                 // one fp32 tile buffer: cin planes of (TH + 2 pad) rows x L0_XP floats
 };
 
+__device__ __forceinline__ void st_y2(float* p, float2 v) {
+  if (SESRQ_X_STCS >= 1) __stcs(reinterpret_cast<float2*>(p), v);
+  else *reinterpret_cast<float2*>(p) = v;
+}
+__device__ __forceinline__ void st_q(int8_t* p, int v) {
+  if (SESRQ_X_STCS >= 2) __stcs(reinterpret_cast<char*>(p), (char)v);
+  else *p = (int8_t)v;
+}
+
 // Stores of the final layer for one pixel: COUT int8 codes to the NCHW q5 planes (stride HW bytes) and the
 // de-quantised values to the pixel-shuffled fp32 output (PixelShuffle(RS): channel n -> plane n / RS^2, row offset
 // (n % RS^2) / RS, column offset n % RS; the RS values of one row are contiguous -> one vector store).
-template <int COUT, int RS>
+template <int COUT, int RS, bool Q, bool Y>
 __device__ __forceinline__ void final_store(const int (&code)[16], const float (&o)[16], int8_t* __restrict__ qb,
-                                            float* __restrict__ yb, const long long HW, const long long plane, const int Wr) {
+                                            float* __restrict__ yb, const long long HW, const long long plane, const int Wr,
+                                            const bool valid) {
   constexpr int R2 = RS * RS;
-  if (qb) {
+  if (Q) {
     int8_t* p = qb;
 #pragma unroll
-    for (int n = 0; n < COUT; ++n, p += HW) *p = (int8_t)code[n];
+    for (int n = 0; n < COUT; ++n, p += HW)
+      if (valid) *p = (int8_t)code[n];
   }
-  if (yb) {
+  if (Y) {
 #pragma unroll
     for (int c = 0; c < COUT / R2; ++c) {
       float* pc = yb + c * plane;
@@ -270,9 +314,11 @@ __device__ __forceinline__ void final_store(const int (&code)[16], const float (
       for (int i = 0; i < RS; ++i) {
         float* dst = pc + (long long)i * Wr;
         const int n0 = c * R2 + i * RS;
-        if constexpr (RS == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[n0], o[n0 + 1], o[n0 + 2], o[n0 + 3]);
-        else if constexpr (RS == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[n0], o[n0 + 1]);
-        else *dst = o[n0];
+        if (valid) {
+          if constexpr (RS == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[n0], o[n0 + 1], o[n0 + 2], o[n0 + 3]);
+          else if constexpr (RS == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[n0], o[n0 + 1]);
+          else *dst = o[n0];
+        }
       }
     }
   }
@@ -301,7 +347,8 @@ __device__ __forceinline__ void final_math(const UmmaParams& P, const float2 (&y
 // straight from its register pair (no staging arrays, no register moves).
 template <bool Q, bool Y>
 __device__ __forceinline__ void final_x2(const UmmaParams& P, const float2 (&yv)[8], int8_t* __restrict__ qb,
-                                         float* __restrict__ yb, const long long HW, const long long plane, const int Wr) {
+                                         float* __restrict__ yb, const long long HW, const long long plane, const int Wr,
+                                         const bool valid) {
   int8_t* qp = qb;
   float* yp = yb;
 #pragma unroll
@@ -311,12 +358,15 @@ __device__ __forceinline__ void final_x2(const UmmaParams& P, const float2 (&yv)
     t.y = fminf(fmaxf(t.y, -128.f), 127.f);
     const float2 rm = f2_add(t, MAGIC_F);
     if (Q) {
-      qp[0] = (int8_t)__float_as_int(rm.x);
-      qp[HW] = (int8_t)__float_as_int(rm.y);
+      if (valid) {
+        st_q(qp, __float_as_int(rm.x));
+        st_q(qp + HW, __float_as_int(rm.y));
+      }
       qp += 2 * HW;
     }
     if (Y) {
-      *reinterpret_cast<float2*>(yp) = f2_mul(f2_add(rm, P.out_off), P.s_out);
+      const float2 ov = f2_mul(f2_add(rm, P.out_off), P.s_out);
+      if (valid) st_y2(yp, ov);
       yp += (k & 1) ? plane - Wr : Wr;                       // row 0 -> row 1 of the plane -> row 0 of the next plane
     }
   }
@@ -329,39 +379,35 @@ __device__ __forceinline__ void final_x2(const UmmaParams& P, const float2 (&yv)
 // ------------------------------------------------------------------------------------------------
 // OUTM (final layer): 0 = both outputs may be wanted, decided by the pointers at run time; 1 = q5 only, 2 = y only
 // (compile time: the single-output kernels carry only their own store sequence, which makes them markedly faster).
-template <int NS, int EPI, int RS, int OUTM, bool FLOOR>
+// COUT (final layer): the output channel count when it is one of the reference's networks (x4: 16 with r = 4, x2: 12 with
+// r = 2, NRDM: 3 with r = 1) -- those kernels carry only their own store sequence; 0 = any count, decided at run time.
+template <int NS, int EPI, int RS, int COUT, int OUTM, bool FLOOR>
 __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[NS][16], const uint4 sc,
                                                uint4* __restrict__ out_px, int8_t* __restrict__ qb,
-                                               float* __restrict__ yb, const long long HW, const float relu_floor) {
+                                               float* __restrict__ yb, const long long HW, const float relu_floor,
+                                               const bool valid) {
   // ---- m = bits of the float 12582912 + A,  A = clampAdd(sum_p clampAcc(P_p)) + K  (quan_func.py:370,437,491) ----
-  if (NS == 2) {
-    // the adder-tree clamp is proved inert for this layout; the few PE clamps that can fire are corrected here
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {              // NS = 2 carries at most 4 risky pairs (accumulator_sets)
-      if (j >= P.n_risky) break;
-      const int v = acc[1][j];
-      const int d = clampi(v, P.lo_acc, P.hi_acc) - v;
-      if (d != 0) {                                          // rare: the clamp really fired
-        const int col = P.risky_col[j];
-#pragma unroll
-        for (int n = 0; n < 16; ++n)
-          if (n == col) acc[0][n] += d;
-      }
-    }
-  }
-  if (NS == 1 && EPI == EPI_FINAL) {
-    // spare-column layout (host: spare_column_layout): columns 12 + j hold the risky partial sums
+  // NS = 2 (correction columns in set 1) and the spare-column layout of NS = 1 final layers (columns 12 + j): the
+  // adder-tree clamp is proved inert; the few PE clamps that can fire are corrected here by d = clamp(v) - v on the
+  // column they belong to.  Firing is rare, so the hot path is the test only and the fix-up is kept compact (it indexes
+  // the accumulator by a run-time column: 12 predicated adds per pair instead of an unrolled decision tree, which used
+  // to make up 90 % of this kernel's code).
+  if (NS == 2 || (NS == 1 && EPI == EPI_FINAL)) {
     if (P.n_risky > 0) {
+      int d[4];
+      bool fire = false;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j >= P.n_risky) break;
-        const int v = acc[0][12 + j];
-        if ((unsigned)(v - P.lo_acc) > (unsigned)(P.hi_acc - P.lo_acc)) {   // rare: the clamp really fires
-          const int d = clampi(v, P.lo_acc, P.hi_acc) - v;
+      for (int j = 0; j < 4; ++j) {              // both layouts carry at most 4 risky pairs (accumulator_sets)
+        const int v = (NS == 2) ? acc[NS - 1][j] : acc[0][12 + j];
+        d[j] = (j < P.n_risky) ? clampi(v, P.lo_acc, P.hi_acc) - v : 0;
+        fire |= (d[j] != 0);
+      }
+      if (fire) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
           const int col = P.risky_col[j];
 #pragma unroll
-          for (int n = 0; n < 16; ++n)
-            if (n == col) acc[0][n] += d;
+          for (int n = 0; n < (NS == 2 ? 16 : 12); ++n) acc[0][n] += (n == col) ? d[j] : 0;
         }
       }
     }
@@ -389,30 +435,25 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
     // q5 = clamp(rint(y + z5)); out = (q5 - z5) * s5 (:585,:594); columns are in natural channel order.
     // rint via the 1.5*2^23 trick: rm = 12582912 + q5 exactly, its low byte is the int8 code.
     constexpr int R2 = RS * RS;
+    constexpr bool Q = OUTM != 2, Y = OUTM != 1;           // OUTM 0 is only launched with both pointers (launch_epi)
     int code[16];
     float o[16];
     const long long plane = HW * R2;                       // one pixel-shuffled output plane
     const int Wr = P.W * RS;
-    // the three networks of the reference: x4 (16 channels, r = 4), x2 (12, r = 2), NRDM (3, r = 1); anything else
-    // takes the generic loop
-    if (RS == 4 && P.cout == 16) { final_math<8>(P, yv, code, o); final_store<16, RS>(code, o, qb, yb, HW, plane, Wr); }
-    else if (RS == 2 && P.cout == 12) {
-      if (OUTM == 2) final_x2<false, true>(P, yv, qb, yb, HW, plane, Wr);
-      else if (OUTM == 1) final_x2<true, false>(P, yv, qb, yb, HW, plane, Wr);
-      else if (qb && yb) final_x2<true, true>(P, yv, qb, yb, HW, plane, Wr);
-      else if (yb) final_x2<false, true>(P, yv, qb, yb, HW, plane, Wr);
-      else final_x2<true, false>(P, yv, qb, yb, HW, plane, Wr);
-    }
-    else if (RS == 1 && P.cout == 3) { final_math<2>(P, yv, code, o); final_store<3, RS>(code, o, qb, yb, HW, plane, Wr); }
+    if (RS == 4 && COUT == 16) { final_math<8>(P, yv, code, o); final_store<16, RS, Q, Y>(code, o, qb, yb, HW, plane, Wr, valid); }
+    else if (RS == 2 && COUT == 12) final_x2<Q, Y>(P, yv, qb, yb, HW, plane, Wr, valid);
+    else if (RS == 1 && COUT == 3) { final_math<2>(P, yv, code, o); final_store<3, RS, Q, Y>(code, o, qb, yb, HW, plane, Wr, valid); }
     else {
       final_math<8>(P, yv, code, o);
+      if (Q) {
 #pragma unroll
-      for (int n = 0; n < 16; ++n)
-        if (n < P.cout && qb) qb[(long long)n * HW] = (int8_t)code[n];
-      if (yb) {
+        for (int n = 0; n < 16; ++n)
+          if (n < P.cout && valid) qb[(long long)n * HW] = (int8_t)code[n];
+      }
+      if (Y) {
 #pragma unroll
         for (int n0 = 0; n0 < 16; n0 += RS) {
-          if (n0 < P.cout) {
+          if (n0 < P.cout && valid) {
             float* dst = yb + (long long)(n0 / R2) * plane + (long long)((n0 % R2) / RS) * Wr;
             if constexpr (RS == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[n0], o[n0 + 1], o[n0 + 2], o[n0 + 3]);
             else if constexpr (RS == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[n0], o[n0 + 1]);
@@ -445,7 +486,7 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
       ow[w] = pack4_sat_s8(__float2int_rn(t01.x), __float2int_rn(t01.y), __float2int_rn(t23.x), __float2int_rn(t23.y)) ^
               0x80808080u;
     }
-    *out_px = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    if (valid) *out_px = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   } else {
     uint32_t ow[4];
 #pragma unroll
@@ -454,16 +495,12 @@ __device__ __forceinline__ void epilogue_pixel(const UmmaParams& P, int (&acc)[N
       ow[w] = pack4_sat_s8(__float2int_rn(t0.x), __float2int_rn(t0.y), __float2int_rn(t1.x), __float2int_rn(t1.y)) ^
               0x80808080u;                                                                      // v = q + 128
     }
-    *out_px = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    if (valid) *out_px = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue warps, shared by both kernels.  A row slot cycles:  pre-loaded with c_init (tcgen05.st) + arrive on
-// acc_empty[slot]  ->  the issuer accumulates one 128-pixel output row on top  ->  tcgen05.ld, immediate re-load of
-// c_init, arrive.  Completion is signalled per group of RG consecutive rows of a tile (acc_full ring indexed by the
-// running group counter); warpgroup wg consumes the groups G == wg (mod NWG) and software-pipelines the TMEM loads
-// of a group's rows (row i+1 is in flight while row i is converted and stored).
+// TMEM <-> register helpers of the epilogue
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void reg_fence16(int (&r)[16]) {
   // the values were produced asynchronously (tcgen05.ld): pin every later use behind the preceding wait::ld
@@ -500,7 +537,65 @@ __device__ __forceinline__ void slot_fence(int (&a)[NS][16]) {
   }
 }
 
-template <int NS, int EPI, int RS, int OUTM, bool FLOOR, int EPI_WARPS>
+// Rows of one completion group.  All RG rows are always processed: rows a frame's short bottom tile does not have
+// (i >= cnt) still own pre-armed slots that no MMA touched, so loading and re-arming them is harmless and their stores
+// are predicated off.  The loop therefore carries no row-count branches between the .sync.aligned TMEM instructions and
+// exists once in the code (the final-layer bodies are large; code size matters).
+template <int NS, int EPI, int RS, int COUT, int OUTM, bool FLOOR>
+__device__ __forceinline__ void epilogue_group(const UmmaParams& P, const int cnt, const uint32_t taddr0, const int (&cinit)[NS][16],
+                                               const uint4* __restrict__ sc_row, uint4* __restrict__ orow,
+                                               int8_t* __restrict__ qb, float* __restrict__ yb, const long long HW,
+                                               const float relu_floor, const bool valid, uint64_t* empty_bar, const int lane,
+                                               const int wg) {
+  constexpr int NCOLS = 16 * NS;
+  constexpr int RG = GroupRows<NS>::value;
+  uint4 sc[RG];
+#pragma unroll
+  for (int i = 0; i < RG; ++i) {
+    sc[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (EPI == EPI_RESIDUAL && valid && i < cnt) sc[i] = __ldg(sc_row + (long long)i * P.W);
+  }
+  constexpr bool PIPE = !(X_NOPIPE && EPI == EPI_FINAL);
+  constexpr bool BRANCH = X_BRANCH && EPI == EPI_FINAL;
+  int acc[PIPE ? 2 : 1][NS][16];
+  if (PIPE) slot_load<NS>(taddr0, acc[0]);
+#pragma unroll
+  for (int i = 0; i < RG; ++i) {
+    constexpr int CUR = 0;
+    const int cur = PIPE ? (i & 1) : CUR;
+    if (!PIPE) slot_load<NS>(taddr0 + (uint32_t)(i * NCOLS), acc[0]);
+    tmem_ld_wait();
+    slot_fence<NS>(acc[cur]);
+    if (PIPE && i + 1 < RG) slot_load<NS>(taddr0 + (uint32_t)((i + 1) * NCOLS), acc[(i + 1) & (PIPE ? 1 : 0)]);   // next row in flight
+    slot_store<NS>(taddr0 + (uint32_t)(i * NCOLS), cinit);      // re-arm the slot; awaited once per group
+    const bool v_i = valid && i < cnt;
+    if (SESRQ_X_ROWSYNC == 2 || (SESRQ_X_ROWSYNC == 1 && EPI == EPI_FINAL)) asm volatile("bar.sync %0, 128;" ::"r"(2 + wg) : "memory");
+    if (BRANCH) {
+      if (v_i) epilogue_pixel<NS, EPI, RS, COUT, OUTM, FLOOR>(P, acc[cur], sc[i], orow, qb, yb, HW, relu_floor, true);
+      __syncwarp();
+    } else {
+      epilogue_pixel<NS, EPI, RS, COUT, OUTM, FLOOR>(P, acc[cur], sc[i], orow, qb, yb, HW, relu_floor, v_i);
+    }
+    if (EPI == EPI_FINAL) {
+      if (OUTM != 2) qb += P.W;
+      if (OUTM != 1) yb += (long long)(RS * RS) * P.W;
+    } else {
+      orow += P.W;
+    }
+    if (X_ROWARRIVE) {
+      tmem_st_wait();
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(empty_bar);
+    }
+  }
+}
+
+// Epilogue warps, shared by both kernels.  A row slot cycles:  pre-loaded with c_init (tcgen05.st)  ->  the issuer
+// accumulates one 128-pixel output row on top  ->  tcgen05.ld, immediate re-load of c_init.  Completion (acc_full ring,
+// indexed by the running group counter) and re-arming (acc_empty, one barrier per group of RG slots, 4 arrivals = the
+// warps of the consuming warpgroup) are signalled per group of RG consecutive rows of a tile; warpgroup wg consumes the
+// groups G == wg (mod NWG) and software-pipelines the TMEM loads of a group's rows.
+template <int NS, int EPI, int RS, int COUT, int OUTM, bool FLOOR, int EPI_WARPS, bool PIN>
 __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ewarp, const int lane, const uint32_t tmem_base,
                                                uint64_t* acc_full, uint64_t* acc_empty,
                                                const uint4* __restrict__ shortcut, uint4* __restrict__ out,
@@ -509,6 +604,7 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
   constexpr int NSLOT = TMEM_COLS / NCOLS;
   constexpr int NWG = EPI_WARPS / 4;
   constexpr int RG = GroupRows<NS>::value;
+  constexpr int NGS = NSLOT / RG;               // group slots
   const int wg = ewarp >> 2;                    // warpgroup
   const int quarter = ewarp & 3;                // TMEM lane quarter this warp may access (== warp id % 4)
   const int ox = quarter * 32 + lane;           // pitch == UMMA_M: a slot is one output row of the tile, lane is the column
@@ -521,13 +617,21 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
 #pragma unroll
   for (int p = 0; p < NS; ++p)
 #pragma unroll
-    for (int n = 0; n < 16; ++n) cinit[p][n] = (NS == 2 && p == 1 && n >= 4) ? 0 : P.c_init[p][n];
-  for (int s = wg; s < NSLOT; s += NWG) slot_store<NS>(tq + s * NCOLS, cinit);
+    for (int n = 0; n < 16; ++n) {
+      cinit[p][n] = (NS == 2 && p == 1 && n >= 4) ? 0 : P.c_init[p][n];
+      // PIN keeps the constants in registers: without it the compiler re-reads them from the constant bank before
+      // the re-arms of every group (8 LDC.64); it is only set where the register budget has the room (no spills)
+      if (PIN) asm volatile("" : "+r"(cinit[p][n]));
+    }
+  for (int g = wg; g < NGS; g += NWG)
+#pragma unroll
+    for (int i = 0; i < RG; ++i) slot_store<NS>(tq + (uint32_t)((g * RG + i) * NCOLS), cinit);
   tmem_st_wait();
   tc_fence_before();
   __syncwarp();
   if (lane == 0)
-    for (int s = wg; s < NSLOT; s += NWG) mbar_arrive(&acc_empty[s]);
+    for (int g = wg; g < NGS; g += NWG)
+      for (int i = 0; i < (X_ROWARRIVE ? RG : 1); ++i) mbar_arrive(&acc_empty[g]);
 
   constexpr int GPB = TB / RG;
   const uint32_t nring = (uint32_t)ring_slots(NSLOT, P.TH);
@@ -542,62 +646,33 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
     const int ngrp = tile_groups<RG>(nblk);
     const bool valid = (ox < P.TW) && (gx < P.W);
     const long long pix0 = (long long)b * HW + (long long)y0 * P.W + gx;
-    // final layer: per-tile output bases (row mb adds mb * W bytes / mb * RS * W * RS floats)
+    // final layer: per-tile output bases (row mb adds mb * W bytes / mb * RS^2 * W floats)
     int8_t* qb_tile = nullptr;
     float* yb_tile = nullptr;
     if (EPI == EPI_FINAL) {
       constexpr int R2 = RS * RS;
-      if (q5 && OUTM != 2) qb_tile = q5 + (long long)b * P.cout * HW + (long long)y0 * P.W + gx;
-      if (y && OUTM != 1) yb_tile = y + (long long)b * (P.cout / R2) * (HW * R2) + (long long)y0 * RS * (P.W * RS) + (long long)gx * RS;
+      if (OUTM != 2) qb_tile = q5 + (long long)b * P.cout * HW + (long long)y0 * P.W + gx;
+      if (OUTM != 1) yb_tile = y + (long long)b * (P.cout / R2) * (HW * R2) + (long long)y0 * RS * (P.W * RS) + (long long)gx * RS;
     }
     const int first = (int)((wg + NWG - (G0 % NWG)) % NWG);
     for (int j = first; j < ngrp; j += NWG) {
       const uint32_t G = G0 + j;
       const int mb0 = (j / GPB) * TB + (j % GPB) * RG;          // tile-local group j = band * GPB + group within the band
       const int cnt = min(RG, nblk - mb0);
-      uint4 sc[RG];
-#pragma unroll
-      for (int i = 0; i < RG; ++i) {
-        sc[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (EPI == EPI_RESIDUAL && valid && i < cnt) sc[i] = __ldg(shortcut + pix0 + (long long)(mb0 + i) * P.W);
-      }
+      const uint32_t slot0 = ring.base + (uint32_t)mb0;         // a multiple of RG
+      const uint32_t taddr0 = tq + slot0 * NCOLS;
+      const long long prow = pix0 + (long long)mb0 * P.W;
+      int8_t* const qb = (EPI == EPI_FINAL && OUTM != 2) ? qb_tile + (long long)mb0 * P.W : nullptr;
+      float* const yb = (EPI == EPI_FINAL && OUTM != 1) ? yb_tile + (long long)(mb0 * RS * RS) * P.W : nullptr;
       __syncwarp();                        // the .sync.aligned TMEM accesses below need a converged warp
       mbar_wait(&acc_full[G % NSLOT], (G / NSLOT) & 1);
       tc_fence_after();
-      int acc[2][NS][16];
-      uint32_t slot = ring.base + (uint32_t)mb0;
-      slot_load<NS>(tq + slot * NCOLS, acc[0]);
-      // final layer: output pointers of the group's first row (row i adds i * W bytes / i * RS^2 * W floats)
-      int8_t* const qb_grp = (EPI == EPI_FINAL) ? qb_tile + mb0 * P.W : nullptr;
-      float* const yb_grp = (EPI == EPI_FINAL) ? yb_tile + (long long)(mb0 * RS * RS) * P.W : nullptr;
-#pragma unroll
-      for (int i = 0; i < RG; ++i) {
-        if (i < cnt) {                     // warp-uniform
-          const uint32_t taddr = tq + slot * NCOLS;
-          const uint32_t slot_cur = slot;
-          ++slot;
-          tmem_ld_wait();
-          slot_fence<NS>(acc[i & 1]);
-          if (i + 1 < RG && i + 1 < cnt) slot_load<NS>(tq + slot * NCOLS, acc[(i + 1) & 1]);   // next row in flight
-          if (!(P.dbg & 2)) slot_store<NS>(taddr, cinit);       // re-arm the slot; completion is awaited after the math
-
-          if (valid && !(P.dbg & 1)) {
-            const int mb = mb0 + i;
-            const long long pix = pix0 + (long long)mb * P.W;
-            float* yb = nullptr;
-            int8_t* qb = nullptr;
-            if (EPI == EPI_FINAL) {
-              yb = yb_grp + (long long)(i * RS * RS) * P.W;          // null stays null-ish only if yb_tile was null:
-              qb = qb_grp + i * P.W;                                //   guarded below
-              if (!yb_tile || OUTM == 1) yb = nullptr;
-              if (!qb_tile || OUTM == 2) qb = nullptr;
-            }
-            epilogue_pixel<NS, EPI, RS, OUTM, FLOOR>(P, acc[i & 1], sc[i], out + pix, qb, yb, HW, relu_floor);
-          }
-          tmem_st_wait();                  // warp-collective: every lane's re-arm store has landed
-          tc_fence_before();
-          if (lane == 0) mbar_arrive(&acc_empty[slot_cur]);
-        }
+      epilogue_group<NS, EPI, RS, COUT, OUTM, FLOOR>(P, cnt, taddr0, cinit, shortcut + prow, out + prow, qb, yb, HW, relu_floor, valid,
+                                                     &acc_empty[slot0 / RG], lane, wg);
+      if (!X_ROWARRIVE) {
+        tmem_st_wait();                    // warp-collective: every lane's re-arm stores have landed
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&acc_empty[slot0 / RG]);
       }
     }
     G0 += ngrp;
@@ -626,7 +701,7 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
 //   * a tile's output rows are split into `nbw` bands of TB rows, each issued by its own warp (warps 1..nbw).  A
 //     band's MMAs touch only that band's accumulator slots (edge rows use a sub-range of the B row blocks), so the
 //     warps are independent: no ordering between them, each tracks its own completions;
-//   * slot readiness (acc_empty, one barrier per row slot) is polled once per band by TB lanes at once;
+//   * slot readiness (acc_empty, one barrier per group of RG row slots) is polled once per band by TB / RG lanes at once;
 //   * completion is signalled per GROUP of RG consecutive rows (one tcgen05.commit per group; barrier ring acc_full
 //     indexed by a running group counter); an epilogue warpgroup consumes one group at a time;
 //   * the code for a full band is completely unrolled: every operand is `band base + compile-time offset`.
@@ -687,9 +762,10 @@ __device__ __forceinline__ void mma_issue_band(const int bw, const int lane, con
   constexpr int GPB = TB / RG;
   const int rows = min(TB, nblk - bw * TB);                  // output rows of this band that exist (may be <= 0)
   const uint32_t slot0 = ring.base + (uint32_t)(bw * TB);
-  // ---- all TB slots of the band pre-loaded?  (lane l <-> band row l) ----
+  // ---- all groups of the band pre-loaded?  (lane l < GPB <-> group l of the band; acc_empty is per group of RG slots) ----
   {
-    const uint32_t bar = acc_empty_addr + (slot0 + (uint32_t)(lane & (TB - 1))) * 8u;
+    const int gl = lane & (GPB - 1);
+    const uint32_t bar = acc_empty_addr + (slot0 / RG + (uint32_t)gl) * 8u;
     uint32_t ok;
     do {
       asm volatile(
@@ -699,10 +775,10 @@ __device__ __forceinline__ void mma_issue_band(const int bw, const int lane, con
           : "=r"(ok) : "r"(bar), "r"(ring.par), "r"(MBAR_SUSPEND_NS) : "memory");
     } while (!__all_sync(0xffffffffu, ok != 0u));
     tc_fence_after();
-    // rows the tile does not have: nobody will consume their slot, so complete its phase here (4 = arrivals of a
-    // consuming warpgroup); the slot stays pre-loaded
-    if (lane < TB && lane >= max(rows, 0))
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], 4;" ::"r"(bar) : "memory");
+    // groups the tile does not have: nobody will consume their slots, so complete the phase here (4 = arrivals of a
+    // consuming warpgroup); the slots stay pre-loaded
+    if (lane < GPB && lane * RG >= max(rows, 0))
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(X_ROWARRIVE ? 4 * RG : 4) : "memory");
   }
   if (rows > 0 && elect_one()) {          // elect.sync: the compiler keeps the block on the uniform datapath
     const uint32_t d_band = tmem_base + slot0 * NCOLS;
@@ -731,7 +807,7 @@ __device__ __forceinline__ void mma_issue_band(const int bw, const int lane, con
 // the kernel.  KS: kernel size; NS: accumulator sets (1/2/4, see header); EPI: EpilogueKind; RS: PixelShuffle
 // factor of the final epilogue (1 otherwise); EPI_WARPS: number of epilogue warps.
 // ------------------------------------------------------------------------------------------------
-template <int KS, int NS, int EPI, int RS, int OUTM, bool FLOOR, int EPI_WARPS>
+template <int KS, int NS, int EPI, int RS, int COUT, int OUTM, bool FLOOR, int EPI_WARPS>
 __global__ void __launch_bounds__((CTRL_WARPS + EPI_WARPS) * 32, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ UmmaParams P,
                  const uint8_t* __restrict__ w_img, const uint4* __restrict__ shortcut, uint4* __restrict__ out,
@@ -764,7 +840,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     }
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);          // one elected arrival per epilogue warp of the owning warpgroup
+      mbar_init(&acc_empty[s], X_ROWARRIVE ? 4 * GroupRows<NS>::value : 4);   // one elected arrival per epilogue warp of the consuming warpgroup
     }
     fence_barrier_init();
   }
@@ -821,8 +897,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     }
   } else {
     // ================= epilogue =================
-    epilogue_warps<NS, EPI, RS, OUTM, FLOOR, EPI_WARPS>(P, warp - CTRL_WARPS, lane, tmem_base, acc_full, acc_empty, shortcut, out,
-                                                        q5, y);
+    constexpr bool PIN = !X_NOPIN && NS == 1 && (EPI == EPI_PLAIN || (EPI == EPI_FINAL && OUTM != 0));
+    epilogue_warps<NS, EPI, RS, COUT, OUTM, FLOOR, EPI_WARPS, PIN>(P, warp - CTRL_WARPS, lane, tmem_base, acc_full, acc_empty,
+                                                                   shortcut, out, q5, y);
   }
 
   // ---- teardown ----
@@ -848,7 +925,6 @@ constexpr int L0_BUILD_WARPS = 8;
 constexpr int L0_XP = 136;               // fp32 tile row pitch in floats = TMA box width: 132 pixels + up to 3 of alignment
                                          // (the box must start on a 16-byte boundary: an unaligned inner coordinate faults)
 constexpr int L0_XSTAGES = 4;            // fp32 tile buffers (upper bound; P.xstages are used)
-constexpr int L0_CHUNK = 29;             // operand entries one builder warp pass produces (32 pixels - 3 neighbours)
 
 // x / s with a hoisted reciprocal.  `rcp` is the Newton-refined reciprocal of s; the three operations are
 // exactly the quotient steps of div.rn.f32's fast path (q0 = x*rcp; e = fma(-s, q0, x); q = fma(rcp, e, q0)),
@@ -921,7 +997,7 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     }
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], X_ROWARRIVE ? 4 * GroupRows<NS>::value : 4);
     }
     for (int i = 0; i < L0_XSTAGES; ++i) {
       mbar_init(&x_full[i], 1);
@@ -944,7 +1020,9 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       int xs = 0;
       uint32_t xph = 0;
       for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+#ifdef SESRQ_DEBUG_KNOBS
         if (P.dbg & 512) break;
+#endif
         mbar_wait(&x_empty[xs], xph ^ 1);
         const int b = t / tiles_per_frame;
         const int r = t - b * tiles_per_frame;
@@ -983,8 +1061,8 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     }
   } else if (warp < CTRL_WARPS + EPI_WARPS) {
     // ================= epilogue (shared with the 16-channel kernel, EPI_PLAIN) =================
-    epilogue_warps<NS, EPI_PLAIN, 1, 0, FLOOR, EPI_WARPS>(P, warp - CTRL_WARPS, lane, tmem_base, acc_full, acc_empty, nullptr, out,
-                                                       nullptr, nullptr);
+    epilogue_warps<NS, EPI_PLAIN, 1, 0, 0, FLOOR, EPI_WARPS, false>(P, warp - CTRL_WARPS, lane, tmem_base, acc_full, acc_empty, nullptr,
+                                                                    out, nullptr, nullptr);
   } else {
     // ================= builders =================
     const int bt = threadIdx.x - (CTRL_WARPS + EPI_WARPS) * 32;       // 0 .. 255
@@ -1006,7 +1084,11 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       uint32_t xph = 0;
       for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
         const int r = t % tiles_per_frame;
+#ifdef SESRQ_DEBUG_KNOBS
         const int rows = (P.dbg & 256) ? 0 : min(P.TH, P.H - (r / P.tiles_x) * P.TH) + 2 * PAD;
+#else
+        const int rows = min(P.TH, P.H - (r / P.tiles_x) * P.TH) + 2 * PAD;
+#endif
         const int delta = ((r % P.tiles_x) * P.TW - PAD) & 3;          // pixels the aligned box starts early
         if (lane == 0) {
           mbar_wait(&x_full[xs], xph);
@@ -1139,7 +1221,57 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static bool is_l0_layout(const LayerConst& c) { return c.cin <= 4; }
+// Tuning knobs from the environment, read once per process (first use).  They select among correct variants only; the
+// knock-out masks that produce wrong results exist only in -DSESRQ_DEBUG_KNOBS builds.
+struct Tuning {
+  int nbw = 0, nbw_l0 = 0, nbw_final = 0, l0_no_tma = 0, l0_xstages = 0, dbg = 0;
+  Tuning() {
+    auto geti = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; };
+    nbw = geti("SESRQ_UMMA_NBW");
+    nbw_l0 = geti("SESRQ_UMMA_NBW_L0");
+    nbw_final = geti("SESRQ_UMMA_NBW_FINAL");
+    l0_no_tma = getenv("SESRQ_L0_NO_TMA") ? 1 : 0;
+    l0_xstages = geti("SESRQ_L0_XSTAGES");
+#ifdef SESRQ_DEBUG_KNOBS
+    dbg = geti("SESRQ_UMMA_DBG");
+#endif
+  }
+};
+static const Tuning& tuning() {
+  static const Tuning t;
+  return t;
+}
+
+constexpr int MAX_DEVICES = 64;
+static int sm_count() {
+  static std::atomic<int> cached[MAX_DEVICES];
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < MAX_DEVICES) {
+    const int c = cached[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dev >= 0 && dev < MAX_DEVICES) cached[dev].store(sms, std::memory_order_relaxed);
+  return sms;
+}
+// The dynamic shared memory opt-in is a per-device (per-context) attribute of the kernel: set it once per
+// (kernel instantiation, device).  cudaFuncSetAttribute is idempotent, so a race between two threads is benign.
+// `done`: one bit per device; the caller keeps one variable per kernel instantiation (a function-pointer type is shared
+// by all instantiations with the same signature, so it cannot live in here).
+template <typename Kern>
+static int ensure_smem_optin(Kern kern, int bytes, std::atomic<uint64_t>& done) {
+  int dev = 0;
+  SESRQ_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < MAX_DEVICES && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return SESRQ_OK;
+  SESRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (dev >= 0 && dev < MAX_DEVICES) done.fetch_or(1ull << dev, std::memory_order_release);
+  return SESRQ_OK;
+}
+
+// layer-0 layout: fp32 NCHW frames with cin <= 4 -- only the FIRST layer reads fp32 (a hidden layer with <= 4 channels
+// reads NHWC16 bytes and runs on the generic path)
+static bool is_l0_layout(const LayerConst& c) { return c.first_layer != 0 && c.cin <= 4; }
 
 // explicit max(y, 0) is only needed for a ReLU layer whose consumer's zero point is above -128 (see epilogue_pixel)
 static bool needs_floor(const LayerConst& c) { return c.epi == EPI_PLAIN && c.relu && c.z_next > -128.f; }
@@ -1289,15 +1421,12 @@ int umma_prepare_layer(LayerDev& L, const int8_t* w) {
   return umma_upload(L, img, "umma weight upload");
 }
 
-template <int KS, int NS, int EPI, int RS, int OUTM, bool FLOOR, int EPI_WARPS>
+template <int KS, int NS, int EPI, int RS, int COUT, int OUTM, bool FLOOR, int EPI_WARPS>
 static int launch_one(const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L, const uint8_t* d_shortcut,
                       uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem, cudaStream_t st) {
-  auto kern = conv_umma_kernel<KS, NS, EPI, RS, OUTM, FLOOR, EPI_WARPS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SESRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  auto kern = conv_umma_kernel<KS, NS, EPI, RS, COUT, OUTM, FLOOR, EPI_WARPS>;
+  static std::atomic<uint64_t> optin_done{0};
+  if (int rc = ensure_smem_optin(kern, 227 * 1024, optin_done)) return rc;
   kern<<<grid, (CTRL_WARPS + EPI_WARPS) * 32, smem, st>>>(tmap, P, L.d_wumma, reinterpret_cast<const uint4*>(d_shortcut),
                                                           reinterpret_cast<uint4*>(d_out), d_q5, d_y);
   SESRQ_LAUNCH_CHECK("conv_umma_kernel");
@@ -1308,23 +1437,25 @@ template <int KS, int NS, int EPI_WARPS>
 static int launch_epi(const LayerConst& c, const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L,
                       const uint8_t* d_shortcut, uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem,
                       cudaStream_t st) {
-#define SESRQ_GO(EPI_, RS_, OUTM_, FLOOR_) \
-  return launch_one<KS, NS, EPI_, RS_, OUTM_, FLOOR_, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st)
-#define SESRQ_GO_FINAL(RS_)                              \
-  do {                                                   \
-    if (d_q5 && d_y) SESRQ_GO(EPI_FINAL, RS_, 0, false); \
-    if (d_y) SESRQ_GO(EPI_FINAL, RS_, 2, false);         \
-    SESRQ_GO(EPI_FINAL, RS_, 1, false);                  \
+#define SESRQ_GO(EPI_, RS_, COUT_, OUTM_, FLOOR_) \
+  return launch_one<KS, NS, EPI_, RS_, COUT_, OUTM_, FLOOR_, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st)
+#define SESRQ_GO_FINAL(RS_, COUT_)                              \
+  do {                                                          \
+    if (d_q5 && d_y) SESRQ_GO(EPI_FINAL, RS_, COUT_, 0, false); \
+    if (d_y) SESRQ_GO(EPI_FINAL, RS_, COUT_, 2, false);         \
+    SESRQ_GO(EPI_FINAL, RS_, COUT_, 1, false);                  \
   } while (0)
   if (c.epi == EPI_PLAIN) {
-    if (needs_floor(c)) SESRQ_GO(EPI_PLAIN, 1, 0, true);
-    SESRQ_GO(EPI_PLAIN, 1, 0, false);
+    if (needs_floor(c)) SESRQ_GO(EPI_PLAIN, 1, 0, 0, true);
+    SESRQ_GO(EPI_PLAIN, 1, 0, 0, false);
   }
-  if (c.epi == EPI_RESIDUAL) SESRQ_GO(EPI_RESIDUAL, 1, 0, false);
+  if (c.epi == EPI_RESIDUAL) SESRQ_GO(EPI_RESIDUAL, 1, 0, 0, false);
   if (!d_q5 && !d_y) return SESRQ_EINVAL;
-  if (c.r_shuffle == 4) SESRQ_GO_FINAL(4);
-  if (c.r_shuffle == 2) SESRQ_GO_FINAL(2);
-  SESRQ_GO_FINAL(1);
+  // the reference's three networks get kernels specialised on their channel count; anything else the run-time loop
+  if (c.r_shuffle == 4) { if (c.cout == 16) SESRQ_GO_FINAL(4, 16); SESRQ_GO_FINAL(4, 0); }
+  if (c.r_shuffle == 2) { if (c.cout == 12) SESRQ_GO_FINAL(2, 12); SESRQ_GO_FINAL(2, 0); }
+  if (c.cout == 3) SESRQ_GO_FINAL(1, 3);
+  SESRQ_GO_FINAL(1, 0);
 #undef SESRQ_GO_FINAL
 #undef SESRQ_GO
 }
@@ -1333,11 +1464,7 @@ template <int KS>
 static int launch_ns(int ns, const LayerConst& c, const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L,
                      const uint8_t* d_shortcut, uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem,
                      cudaStream_t st) {
-  if (ns == 1) {
-    static const int epi_warps = getenv("SESRQ_UMMA_EPI_WARPS") ? atoi(getenv("SESRQ_UMMA_EPI_WARPS")) : 16;   // tuning
-    if (epi_warps == 24) return launch_epi<KS, 1, 24>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
-    return launch_epi<KS, 1, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
-  }
+  if (ns == 1) return launch_epi<KS, 1, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
   if (ns == 2) return launch_epi<KS, 2, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
   return launch_epi<KS, 4, 8>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
 }
@@ -1351,7 +1478,7 @@ static TilePlan choose_tiling(int H, int ns, int prefer, int pad, size_t row_byt
   const int nslot = TMEM_COLS / (16 * ns);
   // `prefer` = the caller's measured band count for NS = 1 (see launch_conv_umma / launch_conv_umma_l0)
   int want = (ns == 1) ? prefer : (ns == 2 ? 2 : 1);
-  if (const char* e = getenv("SESRQ_UMMA_NBW")) want = atoi(e);                  // tuning experiments
+  if (tuning().nbw > 0) want = tuning().nbw;                                     // tuning experiments
   want = std::max(1, std::min(want, std::min(3, nslot / TB)));
   const size_t total = 227 * 1024;
   TilePlan best{0, 0, 0, 0, 0};
@@ -1407,12 +1534,9 @@ template <int KS, int NS, int CIN, bool FLOOR, int EPI_WARPS>
 static int launch_l0_one(const CUtensorMap& xmap, const UmmaParams& P, const LayerDev& L, const float* d_x, uint8_t* d_out,
                          int grid, size_t smem, cudaStream_t st) {
   auto kern = conv_umma_l0_kernel<KS, NS, CIN, FLOOR, EPI_WARPS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    // the kernel also has ~4.2 KB of static shared memory; static + dynamic <= 227 KB
-    SESRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 5 * 1024));
-    attr_set = true;
-  }
+  // the kernel also has ~4.2 KB of static shared memory; static + dynamic <= 227 KB
+  static std::atomic<uint64_t> optin_done{0};
+  if (int rc = ensure_smem_optin(kern, 227 * 1024 - 5 * 1024, optin_done)) return rc;
   kern<<<grid, (CTRL_WARPS + EPI_WARPS + L0_BUILD_WARPS) * 32, smem, st>>>(xmap, P, L.d_wumma, d_x, reinterpret_cast<uint4*>(d_out));
   SESRQ_LAUNCH_CHECK("conv_umma_l0_kernel");
   return SESRQ_OK;
@@ -1429,13 +1553,11 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
   const uint32_t w_bytes = (uint32_t)2 * c.k * N * 16;
   // fixed part: weights, barriers, slack for alignment, and the kernel's 4 KB of static shared memory (stage_w)
   const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (2 * MAX_STAGES + 2 * (TMEM_COLS / N) + 2 * L0_XSTAGES) + 64 + 1024 + 5 * 1024;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   // fp32 tiles by TMA need 16-byte aligned rows (W % 4 == 0), a 16-byte aligned base, and x = 0 -> pad code (z0 <= 127)
   EncodeTiledFn encode = get_encode_fn();
   P.x_tma = (encode && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && c.in_zero <= 127.f) ? 1 : 0;
-  if (getenv("SESRQ_L0_NO_TMA")) P.x_tma = 0;
+  if (tuning().l0_no_tma) P.x_tma = 0;
   const size_t per_row_extra = P.x_tma ? (size_t)2 * c.cin * L0_XP * 4 : (size_t)L0_SP * 4;
   // Bands of 8 rows per tile, 2 or 3: the cost is (rows incl. the padding of the last tile) x (cost per row), and per
   // row 3 bands are ~5 % cheaper for RGB input (fewer halo rows to quantise: 1080p x2 0.278 vs 0.292 ms) but ~4 % dearer
@@ -1443,7 +1565,7 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
   // rows, 0.197 vs 0.178 ms).
   const double rows2 = (double)cdiv(H, 2 * TB) * 2 * TB, rows3 = (double)cdiv(H, 3 * TB) * 3 * TB;
   int prefer = (c.cin == 1 ? rows3 * 1.04 < rows2 : rows3 * 0.95 <= rows2) ? 3 : 2;
-  if (const char* e = getenv("SESRQ_UMMA_NBW_L0")) prefer = atoi(e);            // tuning experiments
+  if (tuning().nbw_l0 > 0) prefer = tuning().nbw_l0;                            // tuning experiments
   const TilePlan tp = choose_tiling(H, ns, prefer, pad, (size_t)L0_EP * 16, 8 * 16, per_row_extra, fixed + 256);
   if (tp.stages < 2) return SESRQ_EUNSUPPORTED;
   P.TH = tp.TH;
@@ -1458,7 +1580,7 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
     P.stages = 2;
     const size_t room = 227 * 1024 - fixed - (size_t)P.stages * P.stage_bytes;
     P.xstages = (int)std::min<size_t>(L0_XSTAGES, room / P.xstage_bytes);
-    if (const char* e = getenv("SESRQ_L0_XSTAGES")) P.xstages = std::min(P.xstages, std::max(2, atoi(e)));
+    if (tuning().l0_xstages > 0) P.xstages = std::min(P.xstages, std::max(2, tuning().l0_xstages));
     if (P.xstages < 2) return SESRQ_EUNSUPPORTED;
   } else {
     P.stages = std::min(tp.stages, 3);
@@ -1491,7 +1613,7 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
   for (int ci = 0; ci < c.cin; ++ci) P.pad_word |= (uint32_t)c.pad_byte << (8 * ci);
   P.in_scale = c.in_scale;
   P.in_zero = c.in_zero;
-  if (const char* e = getenv("SESRQ_UMMA_DBG")) P.dbg = atoi(e);
+  P.dbg = tuning().dbg;
   const int grid = std::min(P.num_tiles, sms);
 #define SESRQ_L0_NS(KS_, CIN_)                                                                              \
   do {                                                                                                      \
@@ -1536,16 +1658,13 @@ int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, c
   const int pairs = (c.k + 1) / 2;
   const uint32_t w_bytes = (uint32_t)pairs * 2 * c.k * N * 16;
   const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (2 * MAX_STAGES + 2 * (TMEM_COLS / N)) + 64 + 1024;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   // slack: the last row's rightmost K chunk reaches 2*pad + 1 pixels past the row
   // slack: the last row's rightmost K chunk reaches 2*pad + 1 pixels past the row
   // measured: 16-channel layers are fastest with 2 bands (TH = 16: the 32-slot ring then holds two tiles; 1080p x2 3x3
   // 0.178 vs 0.185 ms with 3 bands); the 16-output x4 final layer with 3 (540x960: 0.909 vs 0.955 ms)
   int prefer = (c.epi == EPI_FINAL && c.r_shuffle == 4) ? 3 : 2;
-  if (c.epi == EPI_FINAL)
-    if (const char* e = getenv("SESRQ_UMMA_NBW_FINAL")) prefer = atoi(e);       // tuning experiments
+  if (c.epi == EPI_FINAL && tuning().nbw_final > 0) prefer = tuning().nbw_final;   // tuning experiments
   const TilePlan tp = choose_tiling(H, ns, prefer, pad, (size_t)UMMA_M * 16, (size_t)(2 * pad + 1) * 16, 0, fixed);
   if (tp.stages < 2) return SESRQ_EUNSUPPORTED;
   P.TH = tp.TH;
@@ -1561,7 +1680,7 @@ int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, c
   // N is OR-ed in per instruction (mma_issue_tile)
   P.idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(UMMA_M >> 4) << 24);
   fill_epilogue_params(P, c, ns);
-  if (const char* e = getenv("SESRQ_UMMA_DBG")) P.dbg = atoi(e);
+  P.dbg = tuning().dbg;
 
   // ---- tensor map over the NHWC16 input viewed as (W*2 x 8-byte, H, B) ----
   CUtensorMap tmap;

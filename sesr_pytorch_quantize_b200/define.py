@@ -5,6 +5,10 @@ Differences from the reference defaults, both deliberate:
   * the seven *_W_FLG dump switches default to False (the reference ships them True and writes ~432 MB of
     ./output_pt dumps per 80x960 frame).  The fused CUDA path never materialises those tensors; set a flag
     to True to get the corresponding reference-format dump from the un-fused per-node path.
+  * RESIDUAL_W_FLG (new): the reference writes output_pt/residual/shortcut_tensor.pt on every sim forward
+    (quan_func.py:546-549) because its layer-4 quantiser re-reads it; here the shortcut stays on the device.  The
+    un-fused per-node path writes the file (when COMPAT_FILES or this flag is set); setting the flag makes a fused
+    graph take that path.
   * COMPAT_FILES (new) keeps the reference's file protocol alive: thresholds are read from / running
     min-max written to ./output_pt/input/input.{i}.*.pt so that test.py's calibration tail and a later
     sim.py run find them.  Set it to False to keep all state in memory (myQL.state).
@@ -39,6 +43,7 @@ BIAS_QUAN_W_FLG = w_flg_c and True         # conv.bias.quan{i}.pt
 OUTPUT_PE_W_FLG = w_flg_c and True         # pe_output{i}_{p}.pt
 OUTPUT_PE_ADD_W_FLG = w_flg_c and True     # pe_add_output{i}.pt
 REQUAN_FACTOR_W_FLG = w_flg_c and True     # requan_{i}_{j}.pt / n_{i}_{j}.pt
+RESIDUAL_W_FLG = w_flg_c and True          # (new) output_pt/residual/shortcut_tensor.pt; the reference writes it always
 
 WEIGHT_W_HIST_PNG = w_flg_c and False
 INPUT_W_HIST_PNG = w_flg_c and False

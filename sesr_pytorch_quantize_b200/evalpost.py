@@ -1,7 +1,8 @@
 """Evaluation post-step of the reference's test.py:128-170 on device: for the x2 model the
 nearest-upsampled input is added OUTSIDE the network (:149-155), the result is clipped to [0, 1] (:157) and compared with
 the ground truth by PSNR -- plain (data_range 1), channel 0 * 255 for the x4 model (:165-166) or BT.601 luma for the x2
-model (rgb_to_yuv :133-136, :167-168).  SSIM (skimage, test.py:172-175) is a third-party routine and is not provided.
+model (rgb_to_yuv :133-136, :167-168).  `ssim` is the structural similarity the script takes from skimage (test.py:172-175),
+restated as a CUDA kernel with skimage's defaults (7 x 7 uniform window, K1 = 0.01, K2 = 0.03, sample covariance).
 """
 from __future__ import annotations
 
@@ -54,3 +55,25 @@ def sr_post(y: torch.Tensor, x: Optional[torch.Tensor] = None, gt: Optional[torc
         else:                                            # compute_psnr(data_range=255, eps), test.py:128-131
             psnr = 10.0 * math.log10((255.0 ** 2) / (mse + eps))
     return out, psnr
+
+
+def ssim(a: torch.Tensor, b: torch.Tensor, data_range: float = 1.0) -> float:
+    """Mean structural similarity of two float32 CUDA images [..., H, W] (any leading plane dimensions: channels and / or
+    batch): skimage.metrics.structural_similarity(a, b, data_range=..., channel_axis=<planes>) with its default window
+    (test.py:172-175 passes HWC numpy arrays with channel_axis=2, or a single plane with multichannel=False)."""
+    if not a.is_cuda or not b.is_cuda:
+        raise _lib.SesrqError("ssim needs CUDA tensors (no CPU fallback)")
+    if a.shape != b.shape or a.dim() < 2:
+        raise _lib.SesrqError("ssim: shapes differ or are not images: %s vs %s" % (tuple(a.shape), tuple(b.shape)))
+    a = a.contiguous().float()
+    b = b.contiguous().float()
+    H, W = a.shape[-2], a.shape[-1]
+    planes = a.numel() // (H * W)
+    if H < 7 or W < 7:
+        raise _lib.SesrqError("win_size exceeds image extent")          # skimage's own message
+    total = torch.zeros(1, dtype=torch.float64, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.load_library().sesrq_op_ssim(_p(a), _p(b), planes, H, W, float(data_range), _p(total),
+                                                C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream))
+    _lib.check(rc, "sesrq_op_ssim")
+    return float(total.item()) / (planes * (H - 6) * (W - 6))

@@ -7,7 +7,7 @@ from models.model_utils_pt import AddOp, CollapsibleLinearBlock, ResidualCollaps
 
 
 class FiveConvNet(nn.Module):
-    def __init__(self, in_channels, out_channels, num_channels, num_lblocks, scaling_factor, sim, shuffle):
+    def __init__(self, in_channels, out_channels, num_channels, num_lblocks, scaling_factor, sim, shuffle, spare_add=False):
         super().__init__()
         self.conv_first = CollapsibleLinearBlock(in_channels=in_channels, out_channels=num_channels,
                                                  tmp_channels=256, kernel_size=5, activation='relu')
@@ -20,6 +20,10 @@ class FiveConvNet(nn.Module):
         self.conv_last = CollapsibleLinearBlock(in_channels=num_channels,
                                                 out_channels=out_channels * scaling_factor ** 2,
                                                 tmp_channels=256, kernel_size=5, activation='identity')
+        if spare_add:
+            # never called by forward(), like upstream (models/nrdm_3.py:30,46); kept because prepare() swaps it for a
+            # QuantAdd whose buffers are keys of the shipped *_qat_G.pth checkpoints
+            self.add_upsampled_input = AddOp()
         if shuffle:
             self.depth_to_space = nn.PixelShuffle(scaling_factor)
         self._sim = sim

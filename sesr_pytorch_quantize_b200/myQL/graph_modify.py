@@ -154,7 +154,7 @@ def _analyse(gm):
 def _dump_flags_set():
     import define
     return any(getattr(define, f, False) for f in ('INPUT_W_FLG', 'BIAS_W_FLG', 'BIAS_QUAN_W_FLG', 'OUTPUT_PE_W_FLG',
-                                                   'OUTPUT_PE_ADD_W_FLG', 'REQUAN_FACTOR_W_FLG'))
+                                                   'OUTPUT_PE_ADD_W_FLG', 'REQUAN_FACTOR_W_FLG', 'RESIDUAL_W_FLG'))
 
 
 def _fused_forward(self, *args, **kwargs):

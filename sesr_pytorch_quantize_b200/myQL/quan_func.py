@@ -3,8 +3,8 @@
 Same public names, signatures and conventions as the reference (exe_mode 0 = fake-quant "staged" float,
 exe_mode 1 = integer sim; tensors are float32 NCHW holding integer codes in mode 1; `func_id` is the conv
 index in graph order, 5 = the output domain).  Differences:
-  * every tensor op runs in libsesrq's CUDA kernels (one per reference callable, include/sesrq.h "stand-alone
-    myQL ops"); tensors must live on a CUDA device -- there is no CPU fallback;
+  * every tensor op runs in libsesrq's CUDA kernels (one per reference callable and exe_mode, include/sesrq.h
+    "stand-alone myQL ops"); tensors must live on a CUDA device -- there is no CPU fallback;
   * inter-node state lives in myQL.state instead of ./output_pt files (files stay as a compat mirror);
   * graphs built by myQL.graph_modify normally do not execute these node functions at all: the complete
     5-layer chain is recognised and replaced by one fused network call (graph_modify.FusedGraphModule).
@@ -59,6 +59,17 @@ def _p(t):
 
 def _stream(t: Tensor):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _tensor_minmax(x: Tensor):
+    """(min, max) of a CUDA tensor as Python floats (sesrq_minmax_update; one D2H of two floats, like the
+    reference's two .item() calls, quan_func.py:177-178)."""
+    mm = torch.tensor([float("inf"), float("-inf")], dtype=torch.float32, device=x.device)
+    lib = _lib.load_library()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sesrq_minmax_update(_p(x), x.numel(), _p(mm), _stream(x)), "sesrq_minmax_update")
+    lo, hi = mm.tolist()
+    return lo, hi
 
 
 def _save(obj, folder, name):
@@ -121,6 +132,27 @@ def _exact_int_conv_forward(conv: nn.Conv2d):
     return forward
 
 
+def _fq_conv_forward(conv: nn.Conv2d, conv_id: int):
+    """Forward of a Conv2d of the exe_mode 0 graph (weights = codes * s_w, input = PE-split (q - z) * s of THIS call's
+    quantiser): exact integer accumulation scaled once by f32(s) * f32(s_w) -- the arithmetic of the fused fake-quant
+    network, so the per-node graph and the fused call agree bit for bit (the reference's library float conv differs in
+    summation order; parity with it is tolerance-based)."""
+    def forward(x):
+        x = _cuda_f32(x, "fake-quant Conv2d")
+        codes = state.weight_codes[conv_id].to(x.device, torch.float32).contiguous()
+        B, cin, H, W = x.shape
+        out = torch.empty((B, codes.shape[0], H, W), dtype=torch.float32, device=x.device)
+        lib = _lib.load_library()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.sesrq_op_conv_fq(_p(x), B, cin, H, W, _p(codes), codes.shape[0], codes.shape[2],
+                                            state.scale(conv_id), state.weight_scale[conv_id], _p(out), _stream(x)),
+                       "sesrq_op_conv_fq")
+        if conv.bias is not None:
+            out = out + conv.bias.detach().to(x.device, torch.float32)[None, :, None, None]
+        return out
+    return forward
+
+
 def quantize_model_weight(model_input: nn.Module, weight_width: int, exe_mode: int):
     """Quantise every nn.Conv2d weight of a (collapsed) model; conv index = order in the state dict
     (reference :128-159)."""
@@ -140,10 +172,11 @@ def quantize_model_weight(model_input: nn.Module, weight_width: int, exe_mode: i
         else:
             raise KeyError('Unsupported state dict type found. (%s)' % name)
     model.load_state_dict(params)
-    if exe_mode == 1:
-        for m in model.modules():
-            if type(m) is nn.Conv2d:
-                m.forward = _exact_int_conv_forward(m)
+    conv_id = 0
+    for m in model.modules():
+        if type(m) is nn.Conv2d:                              # module order == state-dict order of the weights
+            m.forward = _exact_int_conv_forward(m) if exe_mode == 1 else _fq_conv_forward(m, conv_id)
+            conv_id += 1
     return model
 
 
@@ -152,14 +185,25 @@ def quantize_model_weight(model_input: nn.Module, weight_width: int, exe_mode: i
 # ---------------------------------------------------------------------------------------------------
 def quantize_asymmetrical_by_tensor(tensor_input: Tensor, width: int, exe_mode: int, func_id: int = None) -> Tensor:
     """Input quantiser of conv `func_id` (reference :161-293).  exe_mode 1 returns q - max(z, -128)."""
-    if exe_mode == 0:
-        raise _lib.SesrqError(
-            "exe_mode 0 (fake-quant) runs as one fused network call: build the graph with "
-            "myQL.graph_modify.insert_before / insert_bias_bypass (test.py:79-106) or use "
-            "sesr_pytorch_quantize_b200.fq.FakeQuantNet; the per-node float path is not provided")
     x = _cuda_f32(tensor_input, "quantize_asymmetrical_by_tensor")
     lib = _lib.load_library()
     n = x.numel()
+    if exe_mode == 0:
+        # dynamic per-call range (reference :175-215): observe min/max, running min/max, scale/zero, fake-quant
+        lo, hi = _tensor_minmax(x)
+        state.observe(func_id, lo, hi)
+        assert hi != lo, "Input tensor is all equal,{}".format(func_id)
+        quan_max = 2 ** (width - 1) - 1
+        quan_min = 0 - 2 ** (width - 1)
+        scale = (hi - lo) / (quan_max - quan_min)
+        zero = quan_min - round(lo / scale)
+        state.set_threshold(func_id, scale, zero)                       # the reference rewrites the files every call (:211-212)
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.sesrq_op_fakequant(_p(x), n, scale, int(zero), _p(y), _stream(x)), "sesrq_op_fakequant")
+        if INPUT_W_FLG:
+            _save(y, "output_pt/input", "input.{}.pt".format(func_id))
+        return y
     q = torch.empty_like(x)
     u = torch.empty_like(x)
     zero = state.zero(func_id)
@@ -234,11 +278,38 @@ def _pe_merge(input_tensor, conv_weight, acc_bits, add_bits, input_zero, add_con
     return out
 
 
+def _float_clamp_bounds(bits, input_zero, input_scale, weight_scale):
+    """(min, max) of the float-domain emulation of a `bits`-wide accumulator (reference :331-332, :432-433)."""
+    hi = 2 ** (bits - 1) - 1
+    lo = 0 - 2 ** (bits - 1)
+    return (lo - input_zero) * input_scale * weight_scale, (hi - input_zero) * input_scale * weight_scale
+
+
+def _pe_merge_fq(input_tensor, acc_bounds, add_bounds, bias, pe_num):
+    assert len(input_tensor.shape) == 4, 'Expect input tensor dimension: 4, but get %d' % len(input_tensor.shape)
+    x = _cuda_f32(input_tensor, "PE merge")
+    batch, Cout, H, W = x.shape
+    assert batch % pe_num == 0, 'Input batch size %d is not multiples of PE number %d' % (batch, pe_num)
+    B = batch // pe_num
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device)
+    b = None if bias is None else bias.to(x.device, torch.float32).contiguous()
+    lib = _lib.load_library()
+    inf = float("inf")
+    lo_a, hi_a = acc_bounds
+    lo_s, hi_s = add_bounds if add_bounds is not None else (-inf, inf)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sesrq_op_pe_merge_fq(_p(x), B, Cout, H * W, lo_a, hi_a, lo_s, hi_s, _p(b), _p(out), _stream(x)),
+                   "sesrq_op_pe_merge_fq")
+    return out
+
+
 def reshape_ouput_for_hardware_pe(input_tensor: Tensor, conv_weight, width_accum, input_scale, input_zero,
                                   weight_scale, exe_mode, func_id, pe_num: int = 4):
-    """Clamp each PE's partial sum to `width_accum` bits and add the four PEs (reference :320-389, exe_mode 1)."""
-    if exe_mode != 1:
-        raise _lib.SesrqError("reshape_ouput_for_hardware_pe: exe_mode 0 runs fused (see quantize_asymmetrical_by_tensor)")
+    """Clamp each PE's partial sum to `width_accum` bits and add the four PEs (reference :320-389); exe_mode 0 clamps
+    in the float domain (:330-333)."""
+    if exe_mode == 0:
+        return _pe_merge_fq(input_tensor, _float_clamp_bounds(width_accum, input_zero, input_scale, weight_scale),
+                            None, None, pe_num)
     zeros = torch.zeros(input_tensor.shape[1])
     return _pe_merge(input_tensor, conv_weight, width_accum, 31, input_zero, zeros, func_id, pe_num)
 
@@ -254,11 +325,21 @@ def quantize_bias_with_scale(tensor_input: Tensor, bias_scale, bias_width: int, 
 
 
 def PEs_and_bias_adder(input_tensor, bias, pe_add_width, pe_acc_width, bias_width, func_id, pe_num, exe_mode):
-    """PE adder tree + bias (reference :418-493, exe_mode 1): clamp18 per PE, sum, clamp20,
-    + clamp16(bias_q - sum(W) * z)."""
-    if exe_mode != 1:
-        raise _lib.SesrqError("PEs_and_bias_adder: exe_mode 0 runs fused (see quantize_asymmetrical_by_tensor)")
+    """PE adder tree + bias (reference :418-493): clamp18 per PE, sum, clamp20, then exe_mode 1:
+    + clamp16(bias_q - sum(W) * z); exe_mode 0: float-domain clamps and + bias_q * s_x * s_w."""
     s_x, z_x = state.scale(func_id), state.zero(func_id)
+    if exe_mode == 0:
+        s_w = state.weight_scale[func_id]
+        bias_t = torch.tensor(bias, dtype=torch.float32)
+        bias_fq = quantize_bias_with_scale(bias_t, s_x * s_w, bias_width, exe_mode, func_id)
+        state.bias[func_id] = bias_t
+        out = _pe_merge_fq(input_tensor, _float_clamp_bounds(pe_acc_width, z_x, s_x, s_w),
+                           _float_clamp_bounds(pe_add_width, z_x, s_x, s_w), bias_fq, pe_num)
+        import define
+        if getattr(define, "MFLAG", MFLAG) == 3 and func_id == 4:          # NRDM: observe the output as domain 5 (:460-479)
+            lo, hi = _tensor_minmax(out)
+            state.observe(func_id + 1, lo, hi)
+        return out
     codes = state.weight_codes[func_id]
     bias_t = torch.tensor(bias, dtype=torch.float32)
     bq = quantize_bias_with_scale(bias_t, s_x * state.weight_scale[func_id], bias_width, exe_mode, func_id)
@@ -298,5 +379,8 @@ def requan_conv2d_output(input_tensor, func_id, exe_mode):
             rc = lib.sesrq_op_requant(_p(x), x.numel(), m16, n16, _p(y), _p(sc), _stream(x))
             if func_id == 0:
                 state.shortcut = sc                                    # reference :530,:549
+                import define
+                if getattr(define, "COMPAT_FILES", True) or getattr(define, "RESIDUAL_W_FLG", False):   # reference :546-549
+                    _save(sc, "output_pt/residual", "shortcut_tensor.pt")
     _lib.check(rc, "sesrq_op_requant")
     return y

@@ -1,4 +1,3 @@
-import json
 import os
 import sys
 
@@ -22,34 +21,7 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
-class Golden:
-    def __init__(self, name):
-        self.name = name
-        z = np.load(os.path.join(GOLD, name + ".npz"))
-        self.z = {k: z[k] for k in z.files}
-        self.hashes = json.loads(bytes(self.z["hashes_json"]).decode())
-        self.scales = [float(v) for v in self.z["scales"]]
-        self.zeros = [int(v) for v in self.z["zeros"]]
-        self.r = int(self.z["r"])
-        self.pe_add_bit = int(self.z["pe_add_bit"])
-        self.x = self.z["x"]
-        self.wf = [self.z["wf%d" % i] for i in range(5)]
-        self.bf = [self.z["bf%d" % i] for i in range(5)]
-
-    def __getitem__(self, k):
-        return self.z[k]
-
-    def __contains__(self, k):
-        return k in self.z
-
-
-_cache = {}
-
-
-def load_golden(name):
-    if name not in _cache:
-        _cache[name] = Golden(name)
-    return _cache[name]
+from sesr_pytorch_quantize_b200.fixtures import Golden, load_golden  # noqa: E402,F401
 
 
 @pytest.fixture(params=ALL_CASES)

@@ -35,3 +35,26 @@ def test_post_without_ground_truth_and_errors():
         sr_post(y.cpu())
     with pytest.raises(SesrqError):
         sr_post(y, torch.rand(2, 3, 5, 6).cuda())
+
+
+@pytest.mark.parametrize("shape", [(3, 45, 70), (1, 7, 7), (2, 3, 33, 64), (1, 130, 97)])
+def test_ssim_vs_oracle(shape):
+    """SSIM kernel (test.py:172-175, skimage defaults) against the scipy/numpy restatement, incl. the clipped-image
+    regime of the script (values in [0, 1], data_range 1) and a window that exactly fills the image."""
+    from sesr_pytorch_quantize_b200.evalpost import ssim
+    rng = np.random.default_rng(sum(shape))
+    a = rng.random(shape, dtype=np.float32)
+    b = np.clip(a + 0.1 * rng.standard_normal(shape).astype(np.float32), 0, 1)
+    got = ssim(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), data_range=1.0)
+    want = eo.ssim(a.reshape(-1, shape[-2], shape[-1]), b.reshape(-1, shape[-2], shape[-1]), data_range=1.0)
+    assert abs(got - want) <= 1e-9, (got, want)
+    assert abs(ssim(torch.from_numpy(a).cuda(), torch.from_numpy(a).cuda()) - 1.0) <= 1e-12
+
+
+def test_ssim_errors():
+    from sesr_pytorch_quantize_b200 import SesrqError
+    from sesr_pytorch_quantize_b200.evalpost import ssim
+    with pytest.raises(SesrqError):
+        ssim(torch.rand(3, 6, 20).cuda(), torch.rand(3, 6, 20).cuda())
+    with pytest.raises(SesrqError):
+        ssim(torch.rand(3, 16, 20), torch.rand(3, 16, 20))

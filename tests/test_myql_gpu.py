@@ -159,3 +159,71 @@ def test_quan_modules_debug_helpers(fresh_state):
         fresh_state.bias[i] = torch.from_numpy(b)
     y = sesr_forward_sim(torch.from_numpy(g.x).cuda())
     assert np.array_equal(y.cpu().numpy(), g["yout"])
+
+
+@pytest.mark.parametrize("case", SMALL_CASES)
+def test_per_node_fake_quant_graph_equals_fused(case, fresh_state, monkeypatch):
+    """exe_mode 0 node by node (the stand-alone CUDA op of every reference callable: quantiser :175-215, PE split,
+    Conv2d, reshape_ouput_for_hardware_pe :330-333, PEs_and_bias_adder :431-479) must give the fused fake-quant
+    network's output bit for bit, and leave the same observer files."""
+    import define
+    from myQL import quan_func as qf
+    g = load_golden(case)
+    x = torch.from_numpy(g.x).cuda()
+    gm = quantize_graph(collapsed_model(g, sim=False, device="cuda"), 0, pe_add_bit=g.pe_add_bit)
+    assert gm.fusion_plan() == "fq"
+    y_fused = gm(x).cpu().numpy()
+    mm_fused = [(torch.load("output_pt/input/input.%d.min_val.pt" % i), torch.load("output_pt/input/input.%d.max_val.pt" % i))
+                for i in range(6)]
+    fresh_state.reset()
+    for f in os.listdir("output_pt/input"):
+        os.unlink(os.path.join("output_pt/input", f))
+    monkeypatch.setattr(define, "INPUT_W_FLG", True)          # any dump flag selects the per-node path
+    monkeypatch.setattr(qf, "INPUT_W_FLG", True)
+    monkeypatch.setattr(define, "MFLAG", int(g["mflag"]))      # MFLAG 3 observes the last conv's output (:460-479)
+    gm2 = quantize_graph(collapsed_model(g, sim=False, device="cuda"), 0, pe_add_bit=g.pe_add_bit)
+    assert gm2.fusion_plan() == "graph"
+    y_node = gm2(x).cpu().numpy()
+    assert np.array_equal(y_node, y_fused)
+    mm_node = [(torch.load("output_pt/input/input.%d.min_val.pt" % i), torch.load("output_pt/input/input.%d.max_val.pt" % i))
+               for i in range(6)]
+    assert mm_node == mm_fused
+    # the reference also stores this call's scale / zero and (INPUT_W_FLG) the fake-quantised tensor of every domain
+    for i in range(5):
+        lo, hi = mm_node[i]
+        assert torch.load("output_pt/input/input.%d.scale.pt" % i) == (hi - lo) / 255
+        assert os.path.isfile("output_pt/input/input.%d.pt" % i)
+
+
+def test_mode0_stand_alone_callables(fresh_state):
+    from myQL import quan_func as qf
+    gen = torch.Generator().manual_seed(9)
+    x = (torch.rand(1, 3, 9, 13, generator=gen) * 3 - 1).cuda()
+    y = qf.quantize_asymmetrical_by_tensor(x, 8, 0, func_id=2)
+    lo, hi = float(x.min()), float(x.max())
+    s = (hi - lo) / 255
+    z = -128 - round(lo / s)
+    want = (torch.clamp(torch.round(x.cpu() / s + z), -128, 127) - z) * s           # reference :207,:215 on the CPU
+    assert torch.equal(y.cpu(), want)
+    assert fresh_state.scale(2) == s and fresh_state.zero(2) == z
+    with pytest.raises(AssertionError, match="Input tensor is all equal,3"):
+        qf.quantize_asymmetrical_by_tensor(torch.ones(1, 1, 4, 4).cuda(), 8, 0, func_id=3)
+    # reshape_ouput_for_hardware_pe mode 0: float clamp per PE entry, then the four entries are added (:330-333, :386)
+    conv = (torch.randn(4, 2, 3, 3, generator=gen) * 50).cuda()
+    out = qf.reshape_ouput_for_hardware_pe(conv, None, 4, 0.5, -3, 2.0, 0, 0)      # 4-bit accumulator: [-8, 7]
+    fmax, fmin = (7 + 3) * 0.5 * 2.0, (-8 + 3) * 0.5 * 2.0
+    c = torch.clamp(conv.cpu(), fmin, fmax)
+    assert torch.equal(out.cpu(), ((c[0:1] + c[1:2]) + c[2:3]) + c[3:4])
+
+
+def test_sim_per_node_writes_shortcut_file(fresh_state, monkeypatch):
+    import define
+    from myQL import quan_func as qf
+    g = load_golden("x4_small")
+    set_thresholds(fresh_state, g)
+    monkeypatch.setattr(define, "RESIDUAL_W_FLG", True)
+    gm = quantize_graph(collapsed_model(g, sim=True, device="cuda"), 1, pe_add_bit=g.pe_add_bit)
+    assert gm.fusion_plan() == "graph"
+    gm(torch.from_numpy(g.x).cuda())
+    sc = torch.load("output_pt/residual/shortcut_tensor.pt", map_location="cpu")      # reference :546-549
+    assert np.array_equal(sc.numpy(), g["shortcut"])
