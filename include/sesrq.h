@@ -137,9 +137,11 @@ int sesrq_ws_read_act_i8(const SesrqNet* net, const void* d_ws, size_t ws_bytes,
 int sesrq_minmax_update(const float* d_x, size_t n, float* d_mm, void* stream);
 /* d_hist[SESRQ_KL_BINS] (uint64) += histogram of clamp(x, lo, hi), bin = min(B-1, floor((x-lo)*B/(hi-lo))). */
 int sesrq_hist_update(const float* d_x, size_t n, float lo, float hi, unsigned long long* d_hist, void* stream);
-/* KL-entropy threshold search on device (TensorRT-style).  Writes the chosen bin
- * count i in [tgt_bins, nbins] to d_idx[0]; d_kl (required, nbins+1 doubles) receives KL(P||Q) per
- * candidate i (entries below tgt_bins are untouched). */
+/* KL-entropy threshold search on device: the published NVIDIA pytorch-quantization / TensorRT entropy calibrator
+ * (`_compute_amax_entropy`: h[0] := h[1], source bin k -> target group floor(k * tgt / i), outliers folded into the
+ * last kept bin, last minimum wins; restated in oracle/kl_oracle.py).  Writes the chosen bin count i in
+ * [tgt_bins, nbins] to d_idx[0]; d_kl (required, nbins+1 doubles) receives KL(P||Q) per candidate i (entries below
+ * tgt_bins are untouched).  Clipping threshold = lo + i * (hi - lo) / nbins. */
 int sesrq_kl_threshold(const unsigned long long* d_hist, int nbins, int tgt_bins, int32_t* d_idx,
                        double* d_kl, void* stream);
 

@@ -46,8 +46,9 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def kl_threshold_from_index(idx: int, lo: float, hi: float, bins: int = _lib.KL_BINS) -> float:
-    """Upper clipping threshold for the chosen bin count: centre of the first excluded bin."""
-    return lo + (idx + 0.5) * (hi - lo) / bins
+    """Upper clipping threshold for the chosen bin count: the upper edge of the last kept bin (`calib_bin_edges[i]` of the
+    published calibrator, pytorch-quantization calib/histogram.py)."""
+    return lo + idx * (hi - lo) / bins
 
 
 def thresholds_from_kl(mins: Sequence[float], maxs: Sequence[float], idx: Sequence[int], width: int = QUAN_BIT):

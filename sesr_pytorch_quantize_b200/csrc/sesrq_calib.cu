@@ -2,8 +2,8 @@
 //   min/max  : the observer inside quantize_asymmetrical_by_tensor exe_mode 0 (quan_func.py:175-196)
 //              and myMinMaxObserver (quan_modules.py:14-40)
 //   histogram + KL : the reference abandoned KL calibration (define.py:16-20, BINS_NUM=2048,
-//              TGT_BINS_NUM=128 survive as comments); the spec implemented here is SURVEY.md App. C,
-//              restated on the CPU in oracle/kl_oracle.py ("parity unpinned" w.r.t. the reference).
+//              TGT_BINS_NUM=128 survive as comments); the search implemented here is the published NVIDIA
+//              pytorch-quantization / TensorRT entropy calibrator, restated on the CPU in oracle/kl_oracle.py.
 #include <algorithm>
 #include "sesrq_internal.h"
 
@@ -112,9 +112,12 @@ __global__ void __launch_bounds__(256) hist_kernel(const float* __restrict__ x, 
 }
 
 // ---- KL threshold search ----------------------------------------------------------------------------
-// One CTA per candidate bin count i in [tgt, nbins].  P = hist[0:i] with the outlier mass folded into
-// bin i-1; Q = hist[0:i] merged into `tgt` groups of m = i / tgt bins (the last group takes the
-// remainder) and spread uniformly over the non-empty bins of each group; KL(P||Q) in fp64.
+// The published entropy calibrator (NVIDIA pytorch-quantization `_compute_amax_entropy` = TensorRT entropy calibration
+// 2; restated in oracle/kl_oracle.py), sized by the reference's surviving constants (define.py:19-20).
+// One CTA per candidate bin count i in [tgt, nbins].  h[0] := h[1]; P = h[0:i] with the outlier mass folded into
+// bin i-1; Q = h[0:i] merged into `tgt` groups -- source bin k belongs to group floor(k * tgt / i), i.e. group g covers
+// [ceil(g i / tgt), ceil((g + 1) i / tgt)) -- and spread uniformly over the non-empty bins of each group; KL(P||Q) in
+// fp64.  Every CTA builds the two prefix arrays in shared memory with a block scan (8 bins per thread).
 constexpr int KL_THREADS = 256;
 
 __global__ void __launch_bounds__(KL_THREADS) kl_kernel(const unsigned long long* __restrict__ hist, int nbins,
@@ -123,26 +126,46 @@ __global__ void __launch_bounds__(KL_THREADS) kl_kernel(const unsigned long long
   unsigned long long* s_pref = s_mem;                       // nbins + 1 prefix sums of counts
   unsigned int* s_nz = reinterpret_cast<unsigned int*>(s_pref + nbins + 1);   // nbins + 1 prefix of non-empty flags
   __shared__ double s_red[KL_THREADS / 32];
+  __shared__ unsigned long long s_wsum[KL_THREADS / 32];
+  __shared__ unsigned int s_wnz[KL_THREADS / 32];
   const int i = tgt + blockIdx.x;
-  // prefix sums (serial over 2048 entries by one thread is ~2k adds: negligible, and deterministic)
-  if (threadIdx.x == 0) {
+  // ---- block scan: thread t owns bins [t * per, (t + 1) * per) ----
+  {
+    const int per = (nbins + KL_THREADS - 1) / KL_THREADS;
+    const int k0 = threadIdx.x * per;
     unsigned long long a = 0;
     unsigned int z = 0;
-    s_pref[0] = 0;
-    s_nz[0] = 0;
-    for (int k = 0; k < nbins; ++k) {
-      unsigned long long h = hist[k];
+    for (int k = k0; k < min(k0 + per, nbins); ++k) {
+      const unsigned long long h = hist[(k == 0 && nbins > 1) ? 1 : k];      // h[0] := h[1]
       a += h;
       z += (h != 0);
-      s_pref[k + 1] = a;
-      s_nz[k + 1] = z;
+    }
+    unsigned long long ia = a;                              // inclusive scan over the warp
+    unsigned int iz = z;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long ta = __shfl_up_sync(0xffffffffu, ia, o);
+      const unsigned int tz = __shfl_up_sync(0xffffffffu, iz, o);
+      if ((threadIdx.x & 31) >= o) { ia += ta; iz += tz; }
+    }
+    if ((threadIdx.x & 31) == 31) { s_wsum[threadIdx.x >> 5] = ia; s_wnz[threadIdx.x >> 5] = iz; }
+    __syncthreads();
+    unsigned long long base = ia - a;
+    unsigned int basez = iz - z;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) { base += s_wsum[w]; basez += s_wnz[w]; }
+    if (threadIdx.x == 0) { s_pref[0] = 0; s_nz[0] = 0; }
+    for (int k = k0; k < min(k0 + per, nbins); ++k) {
+      const unsigned long long h = hist[(k == 0 && nbins > 1) ? 1 : k];
+      base += h;
+      basez += (h != 0);
+      s_pref[k + 1] = base;
+      s_nz[k + 1] = basez;
     }
   }
   __syncthreads();
   const unsigned long long total = s_pref[nbins];
   const unsigned long long inside = s_pref[i];
   const unsigned long long outliers = total - inside;
-  const int m = i / tgt;
   double acc = 0.0;
   bool infinite = false;
   if (total != 0 && inside != 0) {
@@ -153,9 +176,9 @@ __global__ void __launch_bounds__(KL_THREADS) kl_kernel(const unsigned long long
       unsigned long long pk = h + ((k == i - 1) ? outliers : 0ull);
       if (pk == 0) continue;
       if (h == 0) { infinite = true; continue; }            // P > 0 where Q == 0
-      int g = min(k / m, tgt - 1);
-      int start = g * m;
-      int stop = (g == tgt - 1) ? i : start + m;
+      const long long g = ((long long)k * tgt) / i;
+      const int start = (int)((g * i + tgt - 1) / tgt);
+      const int stop = (int)(((g + 1) * i + tgt - 1) / tgt);
       unsigned long long gs = s_pref[stop] - s_pref[start];
       unsigned int gn = s_nz[stop] - s_nz[start];
       double p = (double)pk * inv_total;
@@ -178,15 +201,16 @@ __global__ void __launch_bounds__(KL_THREADS) kl_kernel(const unsigned long long
   }
 }
 
+// the published tie-break: the LAST (largest i) minimum; all-infinite -> keep the full range
 __global__ void __launch_bounds__(256) kl_argmin_kernel(const double* __restrict__ kl, int nbins, int tgt,
                                                         int32_t* __restrict__ idx) {
   __shared__ double s_v[256];
   __shared__ int s_i[256];
   double best = INFINITY;
-  int bi = nbins;                                           // all-infinite -> keep the full range
+  int bi = nbins;
   for (int i = tgt + threadIdx.x; i <= nbins; i += blockDim.x) {
     double v = kl[i];
-    if (v < best) { best = v; bi = i; }                     // strided scan keeps the smallest i per thread
+    if (v < best || (v == best && v != INFINITY)) { best = v; bi = i; }   // ascending scan: ties keep the larger i
   }
   s_v[threadIdx.x] = best;
   s_i[threadIdx.x] = bi;
@@ -195,7 +219,7 @@ __global__ void __launch_bounds__(256) kl_argmin_kernel(const double* __restrict
     if (threadIdx.x < o) {
       double v = s_v[threadIdx.x + o];
       int j = s_i[threadIdx.x + o];
-      if (v < s_v[threadIdx.x] || (v == s_v[threadIdx.x] && j < s_i[threadIdx.x])) {
+      if (v < s_v[threadIdx.x] || (v == s_v[threadIdx.x] && v != INFINITY && j > s_i[threadIdx.x])) {
         s_v[threadIdx.x] = v;
         s_i[threadIdx.x] = j;
       }

@@ -13,7 +13,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), PKG):
         sys.path.insert(0, p)
 
 ALL_CASES = ["x4_fixture", "nrdm_fixture", "x2_fixture", "x4_small", "nrdm_small", "x2_small",
-             "synth_clamp", "synth_zero", "synth_neg"]
+             "synth_clamp", "synth_zero", "synth_neg", "nr_small", "dm_small"]
 SMALL_CASES = [c for c in ALL_CASES if not c.endswith("_fixture")]
 
 
@@ -38,12 +38,21 @@ def golden_small(request):
 MODEL_OF_MFLAG = {3: ("nrdm_3_sim", "nrdm_3", "nr"), 5: ("sesr_sim", "sesr", "sesr"), 6: ("sesr_arch_sim", "sesr_arch", "sesr")}
 
 
+# the denoise-only / demosaic-only checkpoints: float variants are models.nr.nr / models.dm.dm (test.py:29-36), the
+# integer-sim variant is the NRDM one (same architecture without the AddOp; upstream has no nr_sim / dm_sim)
+MODEL_OF_CASE = {"nr_small": (("nrdm_3_sim", "nr"), ("nr", "nr")), "dm_small": (("nrdm_3_sim", "nr"), ("dm", "dm"))}
+
+
 def collapsed_model(g, sim, device="cpu"):
     """Model of the golden case's family, collapsed, carrying the golden's collapsed float weights."""
     import importlib
     import torch
-    sim_mod, float_mod, cls = MODEL_OF_MFLAG[int(g["mflag"])]
-    mod = importlib.import_module("models." + (sim_mod if sim else float_mod))
+    if g.name in MODEL_OF_CASE:
+        mod_name, cls = MODEL_OF_CASE[g.name][0 if sim else 1]
+    else:
+        sim_mod, float_mod, cls = MODEL_OF_MFLAG[int(g["mflag"])]
+        mod_name = sim_mod if sim else float_mod
+    mod = importlib.import_module("models." + mod_name)
     model = getattr(mod, cls)()
     model.collapse()
     convs = [model.conv_first.conv_expand] + [b.conv_expand for b in model.residual_block] + [model.conv_last.conv_expand]

@@ -1,6 +1,6 @@
 """N > 1 host logic on CPU: world_size-2 gloo processes exercise the frame sharding and the two calibration
 collectives (MAX over [-min, max], SUM over the int64 histograms) of sesr_pytorch_quantize_b200.calib.
-On the GPU box the same code runs over NCCL (bench.py --gpus N, tests/test_multi_gpu.py)."""
+On the GPU box the same code runs over NCCL (bench.py --gpus N, tests/test_multi_gpu.py + tests/multi_gpu_worker.py)."""
 import os
 import socket
 import sys

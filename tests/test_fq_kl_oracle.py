@@ -41,12 +41,12 @@ def test_histogram_known_answers():
 
 
 def test_kl_search_known_answers():
-    # all mass inside the first 128 bins, uniform: every candidate reproduces P exactly -> KL = 0 from i = 128 on,
-    # smallest i wins
+    # all mass inside the first 128 bins, uniform: every candidate reproduces P exactly -> KL = 0 from i = 128 on;
+    # the published tie-break keeps the LAST minimum
     h = np.zeros(2048, dtype=np.uint64)
     h[:128] = 10
     c = ko.kl_curve(h)
-    assert c[128] == 0.0 and ko.kl_threshold_index(h) == 128
+    assert c[128] == 0.0 and c[2048] == 0.0 and ko.kl_threshold_index(h) == 2048
     assert np.isinf(c[:128]).all()
     # a far outlier bin: candidates that end on an empty bin while outliers exist are infinite (P > 0, Q = 0)
     h2 = h.copy()
@@ -61,8 +61,39 @@ def test_kl_search_known_answers():
     hv = ko.histogram(v, 0.0, float(v.max()))
     i = ko.kl_threshold_index(hv)
     assert 128 < i < 2048
-    assert ko.threshold_value(i, 0.0, 1.0) == (i + 0.5) / 2048
+    assert ko.threshold_value(i, 0.0, 1.0) == i / 2048               # calib_bin_edges[i]
     # scale invariance: multiplying every count by a constant leaves the curve (almost) unchanged
     ca, cb = ko.kl_curve(hv), ko.kl_curve(hv * np.uint64(3))
     fin = np.isfinite(ca)
     assert np.array_equal(fin, np.isfinite(cb)) and np.allclose(ca[fin], cb[fin], rtol=1e-9, atol=1e-12)
+
+
+def test_closed_form_equals_published_algorithm_restated():
+    """kl_curve / kl_threshold_index (what the CUDA kernels follow) against the statement-by-statement restatement of
+    NVIDIA pytorch-quantization's `_compute_amax_entropy` (python loops, np.digitize, scipy.stats.entropy) -- on
+    histograms with a ReLU spike in bin 0, empty bins, a heavy tail, and remainders in the group mapping."""
+    rng = np.random.default_rng(3)
+    cases = []
+    for t in range(3):
+        x = np.abs(rng.standard_normal(60000)).astype(np.float32) * (1 + t)
+        x[rng.random(x.size) < 0.35] = 0                                     # post-ReLU zeros
+        cases.append((ko.histogram(x, 0.0, float(x.max()), bins=512), 512, 32))
+    h = ko.histogram(rng.random(20000).astype(np.float32) ** 3, 0.0, 1.0, bins=300)   # 300 = not a multiple of the target
+    h[40:60] = 0
+    cases.append((h, 300, 16))        # target counts are powers of two (128 in production): np.linspace edges are then exact
+    for hist, bins, tgt in cases:
+        i_ref, div, args = ko.nvidia_entropy_reference(hist, tgt=tgt, start_bin=tgt)
+        curve = ko.kl_curve(hist, bins=bins, tgt=tgt)
+        assert ko.kl_threshold_index(hist, bins=bins, tgt=tgt) == i_ref
+        fin = np.isfinite(div)
+        assert np.array_equal(np.isfinite(curve[tgt:]), fin)
+        assert np.allclose(curve[tgt:][fin], div[fin], rtol=1e-9, atol=1e-12)
+
+
+def test_remainder_is_spread_not_dumped():
+    """The r1 artefact: with m = i // 128 and the remainder in the last group every chosen i was 128k - 1.  The published
+    mapping floor(k * 128 / i) gives group sizes that differ by at most one bin."""
+    for i in (255, 383, 1000, 2047):
+        g = (np.arange(i) * 128) // i
+        sizes = np.bincount(g, minlength=128)
+        assert sizes.max() - sizes.min() <= 1 and sizes.sum() == i

@@ -51,9 +51,12 @@ def test_reference_scripts_run_unmodified(mflag, tmp_path):
     assert int(cal["totalnum"]) == frames and np.isfinite(cal["totalpsnr"]) and np.isfinite(cal["totalssim"])
     scales = [float(cal["scale%d" % i]) for i in range(6)]
     zeros = [int(cal["zero%d" % i]) for i in range(6)]
-    # same frames as the golden's calibration set: thresholds agree with the reference's (its conv is fp32 in library
-    # order, ours integer-exact: ranges to 1e-5 relative)
-    np.testing.assert_allclose(scales, g.scales, rtol=2e-5)
+    # same frames as the golden's calibration set.  The script collapses the expand/squeeze convs on the GPU
+    # (model.cuda() precedes collapse(), sim.py:57,77) with torch's library conv -- TF32 by default on this class of
+    # GPU -- while the golden run collapsed on the CPU: the folded weights differ by ~1e-3 relative, weight codes near a
+    # rounding boundary flip, and the ranges of the later domains move by up to 2e-2 (observed); domain 0 is the input
+    np.testing.assert_allclose(scales, g.scales, rtol=5e-2)
+    assert abs(scales[0] - g.scales[0]) <= 1e-6 * g.scales[0]
     assert zeros == g.zeros
 
     # ---- sim.py: integer hardware simulation with the thresholds test.py just wrote -----------------------------------
@@ -70,5 +73,5 @@ def test_reference_scripts_run_unmodified(mflag, tmp_path):
     # isolated codes on a rounding boundary
     for i in range(5):
         assert np.mean(codes[i] != g["W%d" % i]) <= 0.01
-    if mflag in (3, 5):                       # these load the shipped fixture; MFLAG 6 draws an unseeded torch.rand
-        assert np.array_equal(x, g.x)
+    if mflag == 5:            # loads the shipped SR fixture; MFLAG 3 / 6 run on the unseeded torch.rand the script itself
+        assert np.array_equal(x, g.x)     # draws and saves over rand_DM_Input_80x960.pt (sim.py:197-203)
