@@ -161,13 +161,21 @@ typedef struct SesrqFqDesc {
 typedef struct SesrqFq SesrqFq;
 int sesrq_fq_create(const SesrqFqDesc* desc, SesrqFq** out);
 void sesrq_fq_destroy(SesrqFq* fq);
-size_t sesrq_fq_ws_bytes(const SesrqFq* fq, int H, int W);
-/* One frame [1,Cin,H,W] (the reference path is per-frame dynamic: every domain is quantised with THIS
- * frame's min/max, quan_func.py:177-207).  d_y: float32 [1,Cout/r^2,rH,rW].
- * d_minmax: float[SESRQ_NUM_DOMAINS][2] running (min,max) per domain, updated in place on device.
- * d_frame_minmax (nullable): receives this frame's (min,max) per domain.
+size_t sesrq_fq_ws_bytes(const SesrqFq* fq, int H, int W);                 /* == sesrq_fq_ws_bytes_batch(fq, 1, H, W) */
+size_t sesrq_fq_ws_bytes_batch(const SesrqFq* fq, int B, int H, int W);
+/* B frames [B,Cin,H,W] in one pass (~20 launches for the whole batch).  The reference path is per-frame dynamic:
+ * every domain of every frame is quantised with THAT frame's min/max (quan_func.py:177-207), so frames stay
+ * independent; they are only processed together.  d_y: float32 [B,Cout/r^2,rH,rW].
+ * d_minmax: float[SESRQ_NUM_DOMAINS][2] running (min,max) per domain, updated in place on device (:188-195).
+ * d_frame_minmax (nullable): float[B][SESRQ_NUM_DOMAINS][2], every frame's (min,max) per domain.
  * d_hist (nullable) with d_hist_range float[SESRQ_NUM_DOMAINS][2] = (lo,hi): second calibration pass,
- * adds every domain tensor of this frame to its SESRQ_KL_BINS-bin histogram (uint64[6][2048]). */
+ * adds every domain tensor of every frame to its SESRQ_KL_BINS-bin histogram (uint64[6][2048]).
+ * Kernels: per layer a per-frame constants kernel, an operand quantiser and the tcgen05 convolution with four
+ * PE-masked accumulator sets and the float-domain epilogue (sesrq_umma.cu, EPI_FQ). */
+int sesrq_fq_forward_batch(const SesrqFq* fq, const float* d_x, int B, int H, int W, float* d_y,
+                           float* d_minmax, float* d_frame_minmax, unsigned long long* d_hist,
+                           const float* d_hist_range, void* d_ws, size_t ws_bytes, void* stream);
+/* One frame: sesrq_fq_forward_batch with B = 1. */
 int sesrq_fq_forward(const SesrqFq* fq, const float* d_x, int H, int W, float* d_y,
                      float* d_minmax, float* d_frame_minmax, unsigned long long* d_hist,
                      const float* d_hist_range, void* d_ws, size_t ws_bytes, void* stream);

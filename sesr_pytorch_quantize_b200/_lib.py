@@ -82,7 +82,9 @@ SIGNATURES = {
     "sesrq_fq_create": (_i, [C.POINTER(FqDesc), C.POINTER(_vp)]),
     "sesrq_fq_destroy": (None, [_vp]),
     "sesrq_fq_ws_bytes": (_sz, [_vp, _i, _i]),
+    "sesrq_fq_ws_bytes_batch": (_sz, [_vp, _i, _i, _i]),
     "sesrq_fq_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sesrq_fq_forward_batch": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sesrq_op_quant_first": (_i, [_vp, _sz, _d, _i, _vp, _vp, _vp]),
     "sesrq_op_quant_next": (_i, [_vp, _sz, _i, _vp, _vp, _vp]),
     "sesrq_op_quant_residual": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, _vp, _vp, _vp]),

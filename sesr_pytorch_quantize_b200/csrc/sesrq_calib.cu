@@ -10,25 +10,6 @@
 namespace sesrq {
 
 // ---- running min / max ------------------------------------------------------------------------------
-__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
-  int* a = reinterpret_cast<int*>(addr);
-  int old = *a;
-  while (v < __int_as_float(old)) {
-    int assumed = old;
-    old = atomicCAS(a, assumed, __float_as_int(v));
-    if (old == assumed) break;
-  }
-}
-__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
-  int* a = reinterpret_cast<int*>(addr);
-  int old = *a;
-  while (v > __int_as_float(old)) {
-    int assumed = old;
-    old = atomicCAS(a, assumed, __float_as_int(v));
-    if (old == assumed) break;
-  }
-}
-
 __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x, size_t n, float* __restrict__ mm) {
   float lo = INFINITY, hi = -INFINITY;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,13 +1,23 @@
 // Fake-quant (exe_mode 0) forward: the test.py path (test.py:79-106,146) with per-frame dynamic
-// quantisation of every domain, fused min/max observation and optional KL histograms.
+// quantisation of every domain, fused min/max observation and optional KL histograms -- BATCHED: one pass of
+// ~20 launches processes all B frames (frames are a batch dimension; every frame keeps its own ranges).
 //
 // The reference computes conv((q - z) * s, W * s_w) in fp32 with library-defined summation order
 // (quan_func.py:207-215 feeding nn.Conv2d).  Here the convolution is carried out exactly on the integer
 // operands (q - z) and W and scaled once by f32(s) * f32(s_w); the float-domain emulation of the
 // 18-/20-bit clamps (:330-333, :431-434) and the fake-quant bias (:402,:412,:459) follow the reference
 // op for op.  Parity with the reference on this path is therefore tolerance-based:
-// PSNR >= 60 dB at range 1.0 and max-abs <= 8 * s_5.
+// PSNR >= 60 dB at range 1.0 and max-abs <= 8 * s_5; parity with oracle/fq_oracle.py is bit-exact.
+//
+// Data flow per layer i (all frames at once):
+//   fqb_params_kernel   (min, max) of domain i per frame -> FqFrameParams[B] (scale, zero, clamp bounds, bias; doubles)
+//   fqb_quant_*_kernel  X_i fp32 -> operand bytes b = q + 128 (NHWC16, PE-major byte order); d = q - z = b + dmin
+//   conv_umma_kernel<NS = 4, EPI_FQ>  tcgen05 kind::i8 on the bytes, four PE-masked accumulator sets; epilogue:
+//                       per-PE float products, float clamps, + bias, ReLU, AddOp -> X_{i+1} fp32 NHWC16 + per-frame
+//                       (min, max) of the produced domain (one atomic pair per warp and tile)
+// then the domain-5 fake-quant + PixelShuffle and the fold of the per-frame ranges into the running observer.
 #include <algorithm>
+#include <cmath>
 #include <new>
 #include <vector>
 #include "sesrq_internal.h"
@@ -16,19 +26,12 @@ namespace sesrq {
 
 int launch_hist_dev(const float* d_x, size_t n, const float* d_range, unsigned long long* d_hist, cudaStream_t st);
 
-struct FqLayerDev {
-  int k, cin, cout, relu;
-  int32_t* d_w = nullptr;     // [tap][cin][16 co] int32 codes
-  float* d_bias = nullptr;    // [cout]
-  double w_scale;
-};
-
 // (scale, zero) of one domain from this frame's (min, max): quan_func.py:198-205 in Python doubles
 struct DomQ { double s; double z; float sf; float zf; int degenerate; };
 __device__ __forceinline__ DomQ dom_quant(const float* mm) {
   DomQ d;
   double mn = (double)mm[0], mx = (double)mm[1];
-  d.degenerate = (mx == mn);
+  d.degenerate = !(mx > mn);
   d.s = d.degenerate ? 1.0 : (mx - mn) / 255.0;
   d.z = -128.0 - rint(mn / d.s);        // Python round(): half-to-even on the double
   d.sf = (float)d.s;
@@ -36,167 +39,201 @@ __device__ __forceinline__ DomQ dom_quant(const float* mm) {
   return d;
 }
 
-__global__ void fq_reset_kernel(float* mm_frame) {
-  int i = threadIdx.x;
-  if (i < SESRQ_NUM_DOMAINS) { mm_frame[2 * i] = INFINITY; mm_frame[2 * i + 1] = -INFINITY; }
-}
+constexpr int MM_STRIDE = 2 * SESRQ_NUM_DOMAINS;      // floats per frame: (min, max) of the six domains
 
-// X fp32 [C,H,W] -> (q - z) int16 NHWC16   (quan_func.py:207)
-__global__ void __launch_bounds__(256) fq_quant_kernel(const float* __restrict__ x, int C, int HW,
-                                                       const float* __restrict__ mm, uint4* __restrict__ d16) {
+__global__ void fqb_init_mm_kernel(float* mm, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= HW) return;
-  DomQ dq = dom_quant(mm);
-  uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-  for (int c = 0; c < SESRQ_MAX_CH; ++c) {
-    if (c < C) {
-      int q = quant_add_zero(__fdiv_rn(__ldg(x + (size_t)c * HW + i), dq.sf), dq.zf);
-      int d = q - (int)dq.z;
-      w[c >> 1] |= ((uint32_t)d & 0xffffu) << (16 * (c & 1));
-    }
-  }
-  d16[2 * (size_t)i] = make_uint4(w[0], w[1], w[2], w[3]);
-  d16[2 * (size_t)i + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+  if (i < n) mm[i] = (i & 1) ? -INFINITY : INFINITY;
 }
 
-template <int K>
-__global__ void __launch_bounds__(128)
-fq_conv_kernel(const uint4* __restrict__ d16, const int32_t* __restrict__ wq, const float* __restrict__ bias,
-               int cin, int cout, int relu, double w_scale, int acc_bits, int add_bits,
-               const float* __restrict__ mm_in, const float* __restrict__ residual, float* __restrict__ out,
-               float* __restrict__ mm_out, int H, int W) {
-  constexpr int TAPS = K * K;
-  constexpr int PAD = (K - 1) / 2;
-  extern __shared__ int32_t w_s[];                 // [TAPS][cin][16]
-  __shared__ float s_bias[SESRQ_MAX_CH];
-  __shared__ float s_red[2][4];
-  const int nw = TAPS * cin * 16;
-  for (int i = threadIdx.x; i < nw; i += blockDim.x) w_s[i] = wq[i];
-  const DomQ dq = dom_quant(mm_in);
-  const double bias_scale = dq.s * w_scale;                          // :448
-  if (threadIdx.x < cout) {
-    float bs = (float)bias_scale;
-    float bq = fminf(fmaxf(rintf(__fdiv_rn(bias[threadIdx.x], bs)), -32768.f), 32767.f);   // :402
-    s_bias[threadIdx.x] = __fmul_rn(bq, bs);                         // :412
+// (min, max) of every frame of x [B, per_frame]: grid (chunks, B), one atomic pair per CTA
+__global__ void __launch_bounds__(256) fqb_minmax_frames_kernel(const float* __restrict__ x, size_t per_frame,
+                                                                float* __restrict__ mm) {
+  const float* xf = x + (size_t)blockIdx.y * per_frame;
+  float lo = INFINITY, hi = -INFINITY;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_frame; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = __ldg(xf + i);
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ float s_lo[8], s_hi[8];
+  if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
+    atomic_min_float(mm + (size_t)blockIdx.y * MM_STRIDE, lo);
+    atomic_max_float(mm + (size_t)blockIdx.y * MM_STRIDE + 1, hi);
+  }
+}
+
+// per-frame constants of layer `dom` (dom = 5: only the quantiser of the output domain)
+__global__ void fqb_params_kernel(const float* __restrict__ mm, int dom, int B, double w_scale, const float* __restrict__ bias,
+                                  int cout, int acc_bits, int add_bits, double wpos, double wneg,
+                                  FqFrameParams* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= B) return;
+  const DomQ dq = dom_quant(mm + (size_t)f * MM_STRIDE + 2 * dom);
+  FqFrameParams p;
+  p.in_s = dq.sf;
+  p.in_z = dq.zf;
+  p.degenerate = dq.degenerate;
+  p.pad0 = 0;
+  p.dmin = (int)(-128.0 - dq.z);                                     // == round(min / s)
+  p.cscale = (float)((double)dq.sf * (double)(float)w_scale);
   // float-domain clamp bounds, evaluated in double like the Python expressions (:331-332, :432-433)
   const double hi_a = (double)((1 << (acc_bits - 1)) - 1), lo_a = -(double)(1 << (acc_bits - 1));
   const double hi_s = (double)((1 << (add_bits - 1)) - 1), lo_s = -(double)(1 << (add_bits - 1));
-  const float fmax_a = (float)(((hi_a - dq.z) * dq.s) * w_scale), fmin_a = (float)(((lo_a - dq.z) * dq.s) * w_scale);
-  const float fmax_s = (float)(((hi_s - dq.z) * dq.s) * w_scale), fmin_s = (float)(((lo_s - dq.z) * dq.s) * w_scale);
-  const float cscale = (float)((double)dq.sf * (double)(float)w_scale);
+  p.hi_acc = (float)(((hi_a - dq.z) * dq.s) * w_scale);
+  p.lo_acc = (float)(((lo_a - dq.z) * dq.s) * w_scale);
+  p.hi_add = (float)(((hi_s - dq.z) * dq.s) * w_scale);
+  p.lo_add = (float)(((lo_s - dq.z) * dq.s) * w_scale);
+  // can a clamp fire at all for operands d in [dmin, dmin + 255]?  |P_p| <= up / dn (worst PE of the layer)
+  const double dlo = (double)p.dmin, dhi = dlo + 255.0;
+  const double up = fmax(dhi, 0.0) * wpos + fmax(-dlo, 0.0) * wneg;
+  const double dn = fmax(dhi, 0.0) * wneg + fmax(-dlo, 0.0) * wpos;
+  p.clamp_acc = !(up * (1.0 + 1e-6) + 2.0 < (hi_a - dq.z) && -(dn * (1.0 + 1e-6) + 2.0) > (lo_a - dq.z));
+  p.clamp_add = !(4.0 * up * (1.0 + 1e-6) + 8.0 < (hi_s - dq.z) && -(4.0 * dn * (1.0 + 1e-6) + 8.0) > (lo_s - dq.z));
+  const float bs = (float)(dq.s * w_scale);                            // :448
+#pragma unroll
+  for (int c = 0; c < SESRQ_MAX_CH; ++c) {
+    float v = 0.f;
+    if (c < cout) {
+      const float bq = fminf(fmaxf(rintf(__fdiv_rn(bias[c], bs)), -32768.f), 32767.f);   // :402
+      v = __fmul_rn(bq, bs);                                                             // :412
+    }
+    p.bias[c] = v;
+  }
+  out[f] = p;
+}
 
-  const int HW = H * W;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  float vmin = INFINITY, vmax = -INFINITY;
-  if (pix < HW) {
-    const int xx = pix % W, yy = pix / W;
-    int acc[16][4];
+// operand bytes b = q + 128 in the PE-major byte order (byte j <-> channel (j & 3) * 4 + (j >> 2)), q from THIS frame's
+// scale / zero (:207).  NCHW input (layer 0) and NHWC16 input (layers 1..4).
+__global__ void __launch_bounds__(256) fqb_quant_nchw_kernel(const float* __restrict__ x, int C, int HW, long long npix,
+                                                             const FqFrameParams* __restrict__ fp, uint4* __restrict__ act) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const long long f = i / HW;
+  const int p = (int)(i - f * HW);
+  const float sf = fp[f].in_s, zf = fp[f].in_z;
+  const float* xb = x + f * (long long)C * HW + p;
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int co = 0; co < 16; ++co)
-#pragma unroll
-      for (int p = 0; p < 4; ++p) acc[co][p] = 0;
-#pragma unroll 1
-    for (int dy = 0; dy < K; ++dy) {
-      const int sy = yy + dy - PAD;
-      if (sy < 0 || sy >= H) continue;                               // zero padding of (q - z) * s
-#pragma unroll 1
-      for (int dx = 0; dx < K; ++dx) {
-        const int sx = xx + dx - PAD;
-        if (sx < 0 || sx >= W) continue;
-        const uint4 a = __ldg(d16 + 2 * ((size_t)sy * W + sx));
-        const uint4 b = __ldg(d16 + 2 * ((size_t)sy * W + sx) + 1);
-        const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        const int32_t* wt = w_s + (dy * K + dx) * cin * 16;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          if (c < cin) {
-            const int d = (int)(int16_t)((v[c >> 1] >> (16 * (c & 1))) & 0xffffu);
-            const int4* wc = reinterpret_cast<const int4*>(wt + c * 16);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int4 w4 = wc[g];
-              acc[4 * g + 0][c & 3] += d * w4.x;
-              acc[4 * g + 1][c & 3] += d * w4.y;
-              acc[4 * g + 2][c & 3] += d * w4.z;
-              acc[4 * g + 3][c & 3] += d * w4.w;
-            }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int co = 0; co < 16; ++co) {
-      if (co < cout) {
-        float s = 0.f;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          float yp = __fmul_rn((float)acc[co][p], cscale);
-          yp = fminf(fmaxf(yp, fmin_a), fmax_a);                     // :333
-          s = __fadd_rn(s, yp);                                      // :386
-        }
-        s = fminf(fmaxf(s, fmin_s), fmax_s);                         // :434
-        s = __fadd_rn(s, s_bias[co]);                                // :459
-        if (relu) s = fmaxf(s, 0.f);
-        if (residual) s = __fadd_rn(s, residual[(size_t)co * HW + pix]);   // AddOp (models/sesr.py:45)
-        out[(size_t)co * HW + pix] = s;
-        vmin = fminf(vmin, s);
-        vmax = fmaxf(vmax, s);
-      }
+  for (int c = 0; c < SESRQ_MAX_CH; ++c) {
+    if (c < C) {
+      const int q = quant_add_zero(__fdiv_rn(__ldg(xb + (long long)c * HW), sf), zf);
+      const int j = (c & 3) * 4 + (c >> 2);
+      w[j >> 2] |= (uint32_t)(q + 128) << (8 * (j & 3));
     }
   }
-  // block min/max -> frame min/max of the produced domain
+  act[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(256) fqb_quant_nhwc_kernel(const float4* __restrict__ x, int HW, long long npix,
+                                                             const FqFrameParams* __restrict__ fp, uint4* __restrict__ act) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const long long f = i / HW;
+  const float sf = fp[f].in_s, zf = fp[f].in_z;
+  float v[16];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = __ldg(x + 4 * i + q);
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
   }
-  if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = vmin; s_red[1][threadIdx.x >> 5] = vmax; }
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int q = quant_add_zero(__fdiv_rn(v[c], sf), zf);
+    const int j = (c & 3) * 4 + (c >> 2);
+    w[j >> 2] |= (uint32_t)(q + 128) << (8 * (j & 3));
+  }
+  act[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// 2048-bin histogram of the first `nch` channels of an NHWC16 fp32 tensor over a fixed range (KL pass 2); per-CTA
+// shared bins, warp-aggregated atomics (ReLU outputs pile up in bin 0)
+__global__ void __launch_bounds__(256) fqb_hist_nhwc_kernel(const float* __restrict__ x, size_t n, int nch,
+                                                            const float* __restrict__ d_range,
+                                                            unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int s_hist[SESRQ_KL_BINS];
+  const float lo = d_range[0], hi = d_range[1];
+  if (!(hi > lo)) return;
+  for (int i = threadIdx.x; i < SESRQ_KL_BINS; i += blockDim.x) s_hist[i] = 0u;
   __syncthreads();
-  if (threadIdx.x == 0 && mm_out) {
-    float lo = fminf(fminf(s_red[0][0], s_red[0][1]), fminf(s_red[0][2], s_red[0][3]));
-    float hi = fmaxf(fmaxf(s_red[1][0], s_red[1][1]), fmaxf(s_red[1][2], s_red[1][3]));
-    // float atomics via ordered-int CAS
-    int* a = reinterpret_cast<int*>(mm_out);
-    int old = a[0];
-    while (lo < __int_as_float(old)) { int as = old; old = atomicCAS(a, as, __float_as_int(lo)); if (old == as) break; }
-    old = a[1];
-    while (hi > __int_as_float(old)) { int as = old; old = atomicCAS(a + 1, as, __float_as_int(hi)); if (old == as) break; }
-  }
-}
-
-// domain-5 fake-quant + PixelShuffle (test.py:90-91 maps PixelShuffle to the quantiser; :207-215)
-__global__ void __launch_bounds__(256) fq_final_kernel(const float* __restrict__ x5, int C, int H, int W, int r,
-                                                       int do_quant, const float* __restrict__ mm, float* __restrict__ y) {
-  const int HW = H * W;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)C * HW) return;
-  float v = x5[i];
-  if (do_quant) {
-    DomQ dq = dom_quant(mm);
-    float q = (float)quant_add_zero(__fdiv_rn(v, dq.sf), dq.zf);
-    v = __fmul_rn(__fsub_rn(q, dq.zf), dq.sf);                      // :215
-  }
-  int c = (int)(i / HW);
-  int p = (int)(i - (size_t)c * HW);
-  int yy = p / W, xx = p % W;
-  int r2 = r * r;
-  int cc = c / r2, ii = (c % r2) / r, jj = c % r;
-  y[((size_t)cc * (H * r) + (yy * r + ii)) * (size_t)(W * r) + (xx * r + jj)] = v;
-}
-
-__global__ void fq_commit_kernel(const float* __restrict__ mm_frame, float* __restrict__ mm_run,
-                                 float* __restrict__ mm_frame_out) {
-  int i = threadIdx.x;
-  if (i < SESRQ_NUM_DOMAINS) {
-    float lo = mm_frame[2 * i], hi = mm_frame[2 * i + 1];
-    if (mm_run) {                                                    // quan_func.py:188-195
-      if (lo < mm_run[2 * i]) mm_run[2 * i] = lo;
-      if (hi > mm_run[2 * i + 1]) mm_run[2 * i + 1] = hi;
+  const float scale = __fdiv_rn((float)SESRQ_KL_BINS, __fsub_rn(hi, lo));
+  const size_t n_round = ((n + 31) / 32) * 32;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (size_t)gridDim.x * blockDim.x) {
+    const bool valid = i < n && (int)(i & 15) < nch;
+    const float v = valid ? __ldg(x + i) : 0.f;
+    const float c = fminf(fmaxf(v, lo), hi);
+    int b = (int)floorf(__fmul_rn(__fsub_rn(c, lo), scale));
+    b = min(max(b, 0), SESRQ_KL_BINS - 1);
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const unsigned peers = __match_any_sync(active, b);
+      if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(s_hist + b, __popc(peers));
     }
-    if (mm_frame_out) { mm_frame_out[2 * i] = lo; mm_frame_out[2 * i + 1] = hi; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SESRQ_KL_BINS; i += blockDim.x) {
+    const unsigned int c = s_hist[i];
+    if (c) atomicAdd(hist + i, (unsigned long long)c);
+  }
+}
+
+// domain-5 fake-quant with the frame's range (test.py:90-91 maps PixelShuffle to the quantiser; :207-215) + PixelShuffle:
+// X_5 fp32 NHWC16 -> y fp32 NCHW [B, C / r^2, rH, rW]
+__global__ void __launch_bounds__(256) fqb_final_kernel(const float4* __restrict__ x5, int C, int H, int W, int r, long long npix,
+                                                        int do_quant, const FqFrameParams* __restrict__ fp, float* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const int HW = H * W;
+  const long long f = i / HW;
+  const int p = (int)(i - f * HW);
+  const int yy = p / W, xx = p - yy * W;
+  const float sf = fp[f].in_s, zf = fp[f].in_z;
+  float v[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = __ldg(x5 + 4 * i + q);
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+  const int r2 = r * r;
+  float* yb = y + f * (long long)C * HW;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    if (c < C) {
+      float o = v[c];
+      if (do_quant) {
+        const float q = (float)quant_add_zero(__fdiv_rn(o, sf), zf);
+        o = __fmul_rn(__fsub_rn(q, zf), sf);                      // :215
+      }
+      const int cc = c / r2, ii = (c % r2) / r, jj = c % r;
+      yb[((size_t)cc * (H * r) + (yy * r + ii)) * (size_t)(W * r) + (xx * r + jj)] = o;
+    }
+  }
+}
+
+// fold the per-frame ranges into the running observer (quan_func.py:188-195) and hand them out
+__global__ void fqb_commit_kernel(const float* __restrict__ mm, int B, float* __restrict__ mm_run,
+                                  float* __restrict__ mm_frames_out) {
+  const int d = threadIdx.x;
+  if (d >= SESRQ_NUM_DOMAINS) return;
+  float lo = INFINITY, hi = -INFINITY;
+  for (int f = 0; f < B; ++f) {
+    const float a = mm[(size_t)f * MM_STRIDE + 2 * d], b = mm[(size_t)f * MM_STRIDE + 2 * d + 1];
+    lo = fminf(lo, a);
+    hi = fmaxf(hi, b);
+    if (mm_frames_out) { mm_frames_out[(size_t)f * MM_STRIDE + 2 * d] = a; mm_frames_out[(size_t)f * MM_STRIDE + 2 * d + 1] = b; }
+  }
+  if (mm_run) {
+    if (lo < mm_run[2 * d]) mm_run[2 * d] = lo;
+    if (hi > mm_run[2 * d + 1]) mm_run[2 * d + 1] = hi;
   }
 }
 
@@ -206,19 +243,29 @@ using namespace sesrq;
 
 struct SesrqFq {
   SesrqFqDesc desc;
-  FqLayerDev layers[SESRQ_NUM_LAYERS];
+  LayerDev layers[SESRQ_NUM_LAYERS];          // tcgen05 weight images (4 PE-masked sets)
+  int32_t* d_tapsum[SESRQ_NUM_LAYERS] = {};   // [k*k][64] per-tap, per-PE weight sums in accumulator column order
+  float* d_bias[SESRQ_NUM_LAYERS] = {};
+  double wpos[SESRQ_NUM_LAYERS] = {}, wneg[SESRQ_NUM_LAYERS] = {};
+  size_t chunk_bytes = (size_t)4096 << 20;
 };
 
 namespace {
-struct FqPlan { size_t off_mm, off_d16, off_f[3], total; };
-FqPlan fq_plan(int H, int W) {
+struct FqPlan { int chunk; size_t off_mm, off_fp, off_act, off_x[3], total; };
+FqPlan fq_plan(const SesrqFq* fq, int B, int H, int W) {
   FqPlan p{};
-  size_t hw = (size_t)H * W;
+  const size_t hw = (size_t)H * W;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t per_frame = hw * (16 + 3 * 64) + MM_STRIDE * 4 + sizeof(FqFrameParams);
+  long long c = (long long)(fq->chunk_bytes / std::max<size_t>(per_frame, 1));
+  c = std::max<long long>(1, std::min<long long>(c, std::max(B, 1)));
+  const long long passes = (std::max(B, 1) + c - 1) / c;
+  p.chunk = (int)((std::max(B, 1) + passes - 1) / passes);
   size_t off = 0;
-  p.off_mm = off; off += 256;
-  p.off_d16 = off; off += up(hw * 32);
-  for (int i = 0; i < 3; ++i) { p.off_f[i] = off; off += up(hw * SESRQ_MAX_CH * 4); }
+  p.off_mm = off; off += up((size_t)p.chunk * MM_STRIDE * 4);
+  p.off_fp = off; off += up((size_t)p.chunk * sizeof(FqFrameParams));
+  p.off_act = off; off += up((size_t)p.chunk * hw * 16);
+  for (int i = 0; i < 3; ++i) { p.off_x[i] = off; off += up((size_t)p.chunk * hw * 64); }
   p.total = off;
   return p;
 }
@@ -231,12 +278,14 @@ int sesrq_fq_create(const SesrqFqDesc* d, SesrqFq** out) {
   *out = nullptr;
   if (d->abi_version != SESRQ_ABI_VERSION || d->n_layers != SESRQ_NUM_LAYERS) return SESRQ_EINVAL;
   if (d->r_shuffle < 1 || d->r_shuffle > 4) return SESRQ_EINVAL;
+  if (d->pe_acc_bits < 9 || d->pe_acc_bits > 22 || d->pe_add_bits < 9 || d->pe_add_bits > 30) return SESRQ_EINVAL;
   for (int i = 0; i < SESRQ_NUM_LAYERS; ++i) {
     if ((d->ksize[i] != 3 && d->ksize[i] != 5) || d->cin[i] < 1 || d->cin[i] > SESRQ_MAX_CH || d->cout[i] < 1 ||
         d->cout[i] > SESRQ_MAX_CH || !d->h_weight[i] || !d->h_bias[i])
       return SESRQ_EINVAL;
     if (i > 0 && d->cin[i] != d->cout[i - 1]) return SESRQ_EINVAL;
   }
+  if (d->residual && d->cout[0] != d->cout[3]) return SESRQ_EINVAL;
   if (d->cout[4] % (d->r_shuffle * d->r_shuffle) != 0) return SESRQ_EINVAL;
   int dev = 0;
   SESRQ_CUDA(cudaGetDevice(&dev));
@@ -246,21 +295,49 @@ int sesrq_fq_create(const SesrqFqDesc* d, SesrqFq** out) {
   SesrqFq* fq = new (std::nothrow) SesrqFq();
   if (!fq) return SESRQ_ENOMEM;
   fq->desc = *d;
+  if (const char* e = getenv("SESRQ_FQ_CHUNK_MB")) {
+    long v = atol(e);
+    if (v > 0) fq->chunk_bytes = (size_t)v << 20;
+  }
   for (int i = 0; i < SESRQ_NUM_LAYERS; ++i) {
-    FqLayerDev& L = fq->layers[i];
-    L.k = d->ksize[i]; L.cin = d->cin[i]; L.cout = d->cout[i]; L.relu = d->relu[i]; L.w_scale = d->w_scale[i];
-    const int taps = L.k * L.k;
-    std::vector<int32_t> w((size_t)taps * L.cin * 16, 0);
-    for (int co = 0; co < L.cout; ++co)
-      for (int c = 0; c < L.cin; ++c)
-        for (int t = 0; t < taps; ++t)
-          w[((size_t)t * L.cin + c) * 16 + co] = d->h_weight[i][((size_t)co * L.cin + c) * taps + t];
-    if (cudaMalloc(&L.d_w, w.size() * 4) != cudaSuccess || cudaMalloc(&L.d_bias, L.cout * 4) != cudaSuccess ||
-        cudaMemcpy(L.d_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(L.d_bias, d->h_bias[i], L.cout * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    LayerDev& L = fq->layers[i];
+    LayerConst& c = L.c;
+    memset(&c, 0, sizeof(c));
+    c.k = d->ksize[i]; c.pad = (c.k - 1) / 2; c.cin = d->cin[i]; c.cout = d->cout[i];
+    c.epi = EPI_FQ;
+    c.pe_exact = 1;             // four PE-masked accumulator sets: the float-domain PE sums are rounded one by one
+    c.add_inert = 0;
+    c.relu = d->relu[i];
+    c.r_shuffle = 1;
+    const int8_t* w = d->h_weight[i];
+    const int taps = c.k * c.k;
+    int rc = umma_prepare_layer(L, w);
+    // per-tap, per-PE weight sums (operand-offset correction) and the worst per-PE positive / negative weight mass
+    std::vector<int32_t> ts((size_t)taps * 64, 0);
+    double wpos = 0, wneg = 0;
+    for (int co = 0; co < c.cout; ++co) {
+      double pp[4] = {0, 0, 0, 0}, nn[4] = {0, 0, 0, 0};
+      for (int ci = 0; ci < c.cin; ++ci)
+        for (int t = 0; t < taps; ++t) {
+          const int v = w[((size_t)co * c.cin + ci) * taps + t];
+          ts[(size_t)t * 64 + (ci & 3) * 16 + byte_of_chan(co)] += v;
+          if (v > 0) pp[ci & 3] += v; else nn[ci & 3] -= v;
+        }
+      for (int p = 0; p < 4; ++p) { wpos = std::max(wpos, pp[p]); wneg = std::max(wneg, nn[p]); }
+    }
+    fq->wpos[i] = wpos;
+    fq->wneg[i] = wneg;
+    if (rc == SESRQ_OK &&
+        (cudaMalloc(&fq->d_tapsum[i], ts.size() * 4) != cudaSuccess || cudaMalloc(&fq->d_bias[i], SESRQ_MAX_CH * 4) != cudaSuccess ||
+         cudaMemcpy(fq->d_tapsum[i], ts.data(), ts.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+         cudaMemset(fq->d_bias[i], 0, SESRQ_MAX_CH * 4) != cudaSuccess ||
+         cudaMemcpy(fq->d_bias[i], d->h_bias[i], c.cout * 4, cudaMemcpyHostToDevice) != cudaSuccess)) {
       set_cuda_error(cudaGetLastError(), "fq weight upload");
+      rc = SESRQ_ECUDA;
+    }
+    if (rc != SESRQ_OK) {
       sesrq_fq_destroy(fq);
-      return SESRQ_ECUDA;
+      return rc;
     }
   }
   *out = fq;
@@ -270,74 +347,116 @@ int sesrq_fq_create(const SesrqFqDesc* d, SesrqFq** out) {
 void sesrq_fq_destroy(SesrqFq* fq) {
   if (!fq) return;
   for (int i = 0; i < SESRQ_NUM_LAYERS; ++i) {
-    if (fq->layers[i].d_w) cudaFree(fq->layers[i].d_w);
-    if (fq->layers[i].d_bias) cudaFree(fq->layers[i].d_bias);
+    if (fq->layers[i].d_wumma) cudaFree(fq->layers[i].d_wumma);
+    if (fq->d_tapsum[i]) cudaFree(fq->d_tapsum[i]);
+    if (fq->d_bias[i]) cudaFree(fq->d_bias[i]);
   }
   delete fq;
 }
 
-size_t sesrq_fq_ws_bytes(const SesrqFq* fq, int H, int W) {
-  if (!fq || H <= 0 || W <= 0) return 0;
-  return fq_plan(H, W).total;
+size_t sesrq_fq_ws_bytes_batch(const SesrqFq* fq, int B, int H, int W) {
+  if (!fq || B < 0 || H <= 0 || W <= 0) return 0;
+  return fq_plan(fq, B, H, W).total;
+}
+
+size_t sesrq_fq_ws_bytes(const SesrqFq* fq, int H, int W) { return sesrq_fq_ws_bytes_batch(fq, 1, H, W); }
+
+int sesrq_fq_forward_batch(const SesrqFq* fq, const float* d_x, int B, int H, int W, float* d_y, float* d_minmax,
+                           float* d_frame_minmax, unsigned long long* d_hist, const float* d_hist_range, void* d_ws,
+                           size_t ws_bytes, void* stream) {
+  if (!fq || B < 0 || H <= 0 || W <= 0) return SESRQ_EINVAL;
+  if (B == 0) return SESRQ_OK;
+  if (!d_x || !d_y || !d_ws) return SESRQ_EINVAL;
+  if (d_hist && !d_hist_range) return SESRQ_EINVAL;
+  if ((long long)H * W > (1LL << 27)) return SESRQ_EINVAL;
+  const FqPlan p = fq_plan(fq, B, H, W);
+  if (ws_bytes < p.total) return SESRQ_ENOMEM;
+  if ((reinterpret_cast<uintptr_t>(d_ws) & 15) != 0) return SESRQ_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_ws);
+  float* mm = reinterpret_cast<float*>(ws + p.off_mm);
+  FqFrameParams* fp = reinterpret_cast<FqFrameParams*>(ws + p.off_fp);
+  uint8_t* act = ws + p.off_act;
+  float* X[3] = {reinterpret_cast<float*>(ws + p.off_x[0]), reinterpret_cast<float*>(ws + p.off_x[1]),
+                 reinterpret_cast<float*>(ws + p.off_x[2])};
+  const SesrqFqDesc& D = fq->desc;
+  const int HW = H * W;
+  const int cin = D.cin[0], cout = D.cout[4];
+  const size_t y_frame = (size_t)cout * HW;                 // Cout / r^2 * rH * rW
+  for (int b0 = 0; b0 < B; b0 += p.chunk) {
+    const int nb = std::min(p.chunk, B - b0);
+    const float* x = d_x + (size_t)b0 * cin * HW;
+    const long long npix = (long long)nb * HW;
+    const unsigned pgrid = (unsigned)((npix + 255) / 256);
+    fqb_init_mm_kernel<<<(nb * MM_STRIDE + 255) / 256, 256, 0, st>>>(mm, nb * MM_STRIDE);
+    SESRQ_LAUNCH_CHECK("fqb_init_mm_kernel");
+    {
+      const size_t per_frame = (size_t)cin * HW;                                  // domain 0 (:177-178)
+      dim3 g((unsigned)std::min<size_t>(std::max<size_t>(per_frame / 4096, 1), 64), (unsigned)nb);
+      fqb_minmax_frames_kernel<<<g, 256, 0, st>>>(x, per_frame, mm);
+      SESRQ_LAUNCH_CHECK("fqb_minmax_frames_kernel");
+    }
+    // tensor routing: X_1 = X[0] (kept for the AddOp), X_2 = X[1], X_3 = X[2], X_4 = X[1], X_5 = X[2]
+    const float* in_t[5] = {nullptr, X[0], X[1], X[2], X[1]};
+    float* out_t[5] = {X[0], X[1], X[2], X[1], X[2]};
+    for (int i = 0; i < SESRQ_NUM_LAYERS; ++i) {
+      const LayerDev& L = fq->layers[i];
+      fqb_params_kernel<<<(nb + 127) / 128, 128, 0, st>>>(mm, i, nb, D.w_scale[i], fq->d_bias[i], L.c.cout, D.pe_acc_bits,
+                                                          D.pe_add_bits, fq->wpos[i], fq->wneg[i], fp);
+      SESRQ_LAUNCH_CHECK("fqb_params_kernel");
+      if (i == 0) {
+        if (d_hist) {
+          int rc = launch_hist_dev(x, (size_t)nb * cin * HW, d_hist_range, d_hist, st);
+          if (rc) return rc;
+        }
+        fqb_quant_nchw_kernel<<<pgrid, 256, 0, st>>>(x, cin, HW, npix, fp, reinterpret_cast<uint4*>(act));
+        SESRQ_LAUNCH_CHECK("fqb_quant_nchw_kernel");
+      } else {
+        if (d_hist) {
+          const size_t n = (size_t)npix * 16;
+          const unsigned hg = (unsigned)std::min<size_t>(std::max<size_t>((n + 4095) / 4096, 1), 148 * 4);
+          fqb_hist_nhwc_kernel<<<hg, 256, 0, st>>>(in_t[i], n, L.c.cin, d_hist_range + 2 * i, d_hist + (size_t)i * SESRQ_KL_BINS);
+          SESRQ_LAUNCH_CHECK("fqb_hist_nhwc_kernel");
+        }
+        fqb_quant_nhwc_kernel<<<pgrid, 256, 0, st>>>(reinterpret_cast<const float4*>(in_t[i]), HW, npix, fp,
+                                                     reinterpret_cast<uint4*>(act));
+        SESRQ_LAUNCH_CHECK("fqb_quant_nhwc_kernel");
+      }
+      FqArgs fa{};
+      fa.fp = fp;
+      fa.xout = out_t[i];
+      fa.xres = (i == 3 && D.residual) ? X[0] : nullptr;
+      fa.mm = mm + 2 * (i + 1);
+      fa.tapsum = fq->d_tapsum[i];
+      fa.mm_stride = MM_STRIDE;
+      fa.relu = D.relu[i];
+      fa.cout = L.c.cout;
+      int rc = launch_conv_umma_fq(L, act, fa, nb, H, W, st);
+      if (rc) return rc;
+    }
+    if (d_hist) {
+      const size_t n = (size_t)npix * 16;
+      const unsigned hg = (unsigned)std::min<size_t>(std::max<size_t>((n + 4095) / 4096, 1), 148 * 4);
+      fqb_hist_nhwc_kernel<<<hg, 256, 0, st>>>(X[2], n, cout, d_hist_range + 10, d_hist + (size_t)5 * SESRQ_KL_BINS);
+      SESRQ_LAUNCH_CHECK("fqb_hist_nhwc_kernel");
+    }
+    // SESR: the PixelShuffle input is fake-quantised with this frame's range (test.py:90-91);
+    // NRDM (observe_out): no PixelShuffle node, the conv output is only observed (quan_func.py:460-479)
+    fqb_params_kernel<<<(nb + 127) / 128, 128, 0, st>>>(mm, 5, nb, 1.0, fq->d_bias[4], 0, D.pe_acc_bits, D.pe_add_bits, 0.0, 0.0, fp);
+    SESRQ_LAUNCH_CHECK("fqb_params_kernel");
+    fqb_final_kernel<<<pgrid, 256, 0, st>>>(reinterpret_cast<const float4*>(X[2]), cout, H, W, D.r_shuffle, npix,
+                                            D.observe_out ? 0 : 1, fp, d_y + (size_t)b0 * y_frame);
+    SESRQ_LAUNCH_CHECK("fqb_final_kernel");
+    fqb_commit_kernel<<<1, 32, 0, st>>>(mm, nb, d_minmax, d_frame_minmax ? d_frame_minmax + (size_t)b0 * MM_STRIDE : nullptr);
+    SESRQ_LAUNCH_CHECK("fqb_commit_kernel");
+  }
+  return SESRQ_OK;
 }
 
 int sesrq_fq_forward(const SesrqFq* fq, const float* d_x, int H, int W, float* d_y, float* d_minmax,
                      float* d_frame_minmax, unsigned long long* d_hist, const float* d_hist_range, void* d_ws,
                      size_t ws_bytes, void* stream) {
-  if (!fq || !d_x || !d_y || !d_ws || H <= 0 || W <= 0) return SESRQ_EINVAL;
-  if (d_hist && !d_hist_range) return SESRQ_EINVAL;
-  if ((long long)H * W > (1LL << 27)) return SESRQ_EINVAL;
-  FqPlan p = fq_plan(H, W);
-  if (ws_bytes < p.total) return SESRQ_ENOMEM;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  uint8_t* ws = static_cast<uint8_t*>(d_ws);
-  float* mm = reinterpret_cast<float*>(ws + p.off_mm);
-  uint4* d16 = reinterpret_cast<uint4*>(ws + p.off_d16);
-  float* F[3] = {reinterpret_cast<float*>(ws + p.off_f[0]), reinterpret_cast<float*>(ws + p.off_f[1]),
-                 reinterpret_cast<float*>(ws + p.off_f[2])};
-  const int HW = H * W;
-  const SesrqFqDesc& D = fq->desc;
-
-  fq_reset_kernel<<<1, 32, 0, st>>>(mm);
-  SESRQ_LAUNCH_CHECK("fq_reset_kernel");
-  int rc = sesrq_minmax_update(d_x, (size_t)D.cin[0] * HW, mm, stream);   // domain 0 (:177-178)
-  if (rc) return rc;
-
-  // tensor routing: X0=d_x, X1=F0 (kept for the AddOp), X2=F1, X3=F2, X4=F1, X5=F2
-  const float* in_t[5] = {d_x, F[0], F[1], F[2], F[1]};
-  float* out_t[5] = {F[0], F[1], F[2], F[1], F[2]};
-  for (int i = 0; i < SESRQ_NUM_LAYERS; ++i) {
-    const FqLayerDev& L = fq->layers[i];
-    if (d_hist) {
-      rc = launch_hist_dev(in_t[i], (size_t)L.cin * HW, d_hist_range + 2 * i, d_hist + (size_t)i * SESRQ_KL_BINS, st);
-      if (rc) return rc;
-    }
-    fq_quant_kernel<<<cdiv(HW, 256), 256, 0, st>>>(in_t[i], L.cin, HW, mm + 2 * i, d16);
-    SESRQ_LAUNCH_CHECK("fq_quant_kernel");
-    const float* res = (i == 3 && D.residual) ? F[0] : nullptr;
-    size_t smem = (size_t)L.k * L.k * L.cin * 16 * 4;
-    if (L.k == 3)
-      fq_conv_kernel<3><<<cdiv(HW, 128), 128, smem, st>>>(d16, L.d_w, L.d_bias, L.cin, L.cout, L.relu, L.w_scale,
-                                                         D.pe_acc_bits, D.pe_add_bits, mm + 2 * i, res, out_t[i],
-                                                         mm + 2 * (i + 1), H, W);
-    else
-      fq_conv_kernel<5><<<cdiv(HW, 128), 128, smem, st>>>(d16, L.d_w, L.d_bias, L.cin, L.cout, L.relu, L.w_scale,
-                                                         D.pe_acc_bits, D.pe_add_bits, mm + 2 * i, res, out_t[i],
-                                                         mm + 2 * (i + 1), H, W);
-    SESRQ_LAUNCH_CHECK("fq_conv_kernel");
-  }
-  const int cout = D.cout[4];
-  if (d_hist) {
-    rc = launch_hist_dev(F[2], (size_t)cout * HW, d_hist_range + 10, d_hist + (size_t)5 * SESRQ_KL_BINS, st);
-    if (rc) return rc;
-  }
-  // SESR: the PixelShuffle input is fake-quantised with this frame's range (test.py:90-91);
-  // NRDM (observe_out): no PixelShuffle node, the conv output is only observed (quan_func.py:460-479)
-  fq_final_kernel<<<cdiv(cout * HW, 256), 256, 0, st>>>(F[2], cout, H, W, D.r_shuffle, D.observe_out ? 0 : 1, mm + 10, d_y);
-  SESRQ_LAUNCH_CHECK("fq_final_kernel");
-  fq_commit_kernel<<<1, 32, 0, st>>>(mm, d_minmax, d_frame_minmax);
-  SESRQ_LAUNCH_CHECK("fq_commit_kernel");
-  return SESRQ_OK;
+  return sesrq_fq_forward_batch(fq, d_x, 1, H, W, d_y, d_minmax, d_frame_minmax, d_hist, d_hist_range, d_ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -537,6 +537,83 @@ __device__ __forceinline__ void slot_fence(int (&a)[NS][16]) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// exe_mode 0 (fake-quant) epilogue of one output pixel.  The four accumulator sets hold the per-PE integer partial sums
+// of the operand bytes (pre-armed with MAGIC_BITS, so each word is the float 12582912 + A_p): y_p = f32(A_p) * cscale,
+// float-domain PE clamp, sum of the four PEs, adder clamp, + fake-quantised bias, ReLU, AddOp -- the reference's op order
+// (quan_func.py:330-333, :386, :431-434, :459; models/sesr.py:45), restated in oracle/fq_oracle.py.
+//   SLOW: per-frame operand offset dmin != 0 (the frame's minimum is not code 0: zero padding is then NOT byte 0, so the
+//         in-frame tap sums times dmin are added per pixel) and / or clamps that can fire.  Rare, kept out of line.
+// ------------------------------------------------------------------------------------------------
+template <bool SLOW>
+__device__ __forceinline__ void epilogue_pixel_fq(const FqArgs& fa, const FqFrameParams& f, const int (&acc)[4][16],
+                                                  float* __restrict__ xo, const float* __restrict__ xr, const bool valid,
+                                                  const int gy, const int gx, const int H, const int W, const int ks,
+                                                  float& vmin, float& vmax) {
+  float4 res[4];
+  if (xr != nullptr && valid) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) res[q] = __ldg(reinterpret_cast<const float4*>(xr) + q);
+  }
+  float o[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    const int co = chan_of_byte(n);                    // accumulator column n <-> output channel (PE-major byte order)
+    float a[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) a[p] = __fadd_rn(__int_as_float(acc[p][n]), -MAGIC_F);       // exact: A_p as a float
+    if (SLOW && f.dmin != 0) {
+      // d = byte + dmin and out-of-frame d = 0: add dmin * (sum of the PE's weights over the IN-FRAME taps); integer
+      // arithmetic like the oracle's int64 conv, converted to float once
+      const int pad = (ks - 1) / 2;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        long long corr = 0;
+        for (int dy = 0; dy < ks; ++dy) {
+          const int sy = gy + dy - pad;
+          if (sy < 0 || sy >= H) continue;
+          for (int dx = 0; dx < ks; ++dx) {
+            const int sx = gx + dx - pad;
+            if (sx < 0 || sx >= W) continue;
+            corr += fa.tapsum[(dy * ks + dx) * 64 + p * 16 + n];
+          }
+        }
+        a[p] = (float)((long long)__float2int_rn(a[p]) + corr * (long long)f.dmin);
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float yp = __fmul_rn(a[p], f.cscale);
+      if (SLOW) yp = fminf(fmaxf(yp, f.lo_acc), f.hi_acc);                                   // :333
+      s = __fadd_rn(s, yp);                                                                  // :386
+    }
+    if (SLOW) s = fminf(fmaxf(s, f.lo_add), f.hi_add);                                       // :434
+    s = __fadd_rn(s, f.bias[co]);                                                            // :459
+    if (fa.relu) s = fmaxf(s, 0.f);
+    o[co] = s;
+  }
+  if (xr != nullptr) {                                                                       // AddOp (models/sesr.py:45)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      o[4 * q + 0] = __fadd_rn(o[4 * q + 0], res[q].x);
+      o[4 * q + 1] = __fadd_rn(o[4 * q + 1], res[q].y);
+      o[4 * q + 2] = __fadd_rn(o[4 * q + 2], res[q].z);
+      o[4 * q + 3] = __fadd_rn(o[4 * q + 3], res[q].w);
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      if (c < fa.cout) { vmin = fminf(vmin, o[c]); vmax = fmaxf(vmax, o[c]); }
+      else o[c] = 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      reinterpret_cast<float4*>(xo)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  }
+}
+
 // Rows of one completion group.  All RG rows are always processed: rows a frame's short bottom tile does not have
 // (i >= cnt) still own pre-armed slots that no MMA touched, so loading and re-arming them is harmless and their stores
 // are predicated off.  The loop therefore carries no row-count branches between the .sync.aligned TMEM instructions and
@@ -546,7 +623,8 @@ __device__ __forceinline__ void epilogue_group(const UmmaParams& P, const int cn
                                                const uint4* __restrict__ sc_row, uint4* __restrict__ orow,
                                                int8_t* __restrict__ qb, float* __restrict__ yb, const long long HW,
                                                const float relu_floor, const bool valid, uint64_t* empty_bar, const int lane,
-                                               const int wg) {
+                                               const int wg, const FqArgs& fa, const FqFrameParams& fq, const long long fq_px,
+                                               const int gy0, const int gx, float& vmin, float& vmax) {
   constexpr int NCOLS = 16 * NS;
   constexpr int RG = GroupRows<NS>::value;
   uint4 sc[RG];
@@ -570,7 +648,12 @@ __device__ __forceinline__ void epilogue_group(const UmmaParams& P, const int cn
     slot_store<NS>(taddr0 + (uint32_t)(i * NCOLS), cinit);      // re-arm the slot; awaited once per group
     const bool v_i = valid && i < cnt;
     if (SESRQ_X_ROWSYNC == 2 || (SESRQ_X_ROWSYNC == 1 && EPI == EPI_FINAL)) asm volatile("bar.sync %0, 128;" ::"r"(2 + wg) : "memory");
-    if (BRANCH) {
+    if constexpr (EPI == EPI_FQ && NS == 4) {
+      const long long px = fq_px + (long long)i * P.W;
+      const bool slow = (fq.dmin != 0) || fq.clamp_acc || fq.clamp_add;              // per frame: warp-uniform
+      if (slow) epilogue_pixel_fq<true>(fa, fq, acc[cur], fa.xout + px * 16, fa.xres ? fa.xres + px * 16 : nullptr, v_i, gy0 + i, gx, P.H, P.W, 2 * P.pad + 1, vmin, vmax);
+      else epilogue_pixel_fq<false>(fa, fq, acc[cur], fa.xout + px * 16, fa.xres ? fa.xres + px * 16 : nullptr, v_i, gy0 + i, gx, P.H, P.W, 2 * P.pad + 1, vmin, vmax);
+    } else if (BRANCH) {
       if (v_i) epilogue_pixel<NS, EPI, RS, COUT, OUTM, FLOOR>(P, acc[cur], sc[i], orow, qb, yb, HW, relu_floor, true);
       __syncwarp();
     } else {
@@ -599,7 +682,7 @@ template <int NS, int EPI, int RS, int COUT, int OUTM, bool FLOOR, int EPI_WARPS
 __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ewarp, const int lane, const uint32_t tmem_base,
                                                uint64_t* acc_full, uint64_t* acc_empty,
                                                const uint4* __restrict__ shortcut, uint4* __restrict__ out,
-                                               int8_t* __restrict__ q5, float* __restrict__ y) {
+                                               int8_t* __restrict__ q5, float* __restrict__ y, const FqArgs& fa) {
   constexpr int NCOLS = 16 * NS;
   constexpr int NSLOT = TMEM_COLS / NCOLS;
   constexpr int NWG = EPI_WARPS / 4;
@@ -654,6 +737,10 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
       if (OUTM != 2) qb_tile = q5 + (long long)b * P.cout * HW + (long long)y0 * P.W + gx;
       if (OUTM != 1) yb_tile = y + (long long)b * (P.cout / R2) * (HW * R2) + (long long)y0 * RS * (P.W * RS) + (long long)gx * RS;
     }
+    // exe_mode 0: this tile's frame constants, and the running (min, max) of what this warp produces for the frame
+    FqFrameParams fq;
+    float vmin = INFINITY, vmax = -INFINITY;
+    if (EPI == EPI_FQ) fq = fa.fp[b];
     const int first = (int)((wg + NWG - (G0 % NWG)) % NWG);
     for (int j = first; j < ngrp; j += NWG) {
       const uint32_t G = G0 + j;
@@ -668,7 +755,7 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
       mbar_wait(&acc_full[G % NSLOT], (G / NSLOT) & 1);
       tc_fence_after();
       epilogue_group<NS, EPI, RS, COUT, OUTM, FLOOR>(P, cnt, taddr0, cinit, shortcut + prow, out + prow, qb, yb, HW, relu_floor, valid,
-                                                     &acc_empty[slot0 / RG], lane, wg);
+                                                     &acc_empty[slot0 / RG], lane, wg, fa, fq, prow, y0 + mb0, gx, vmin, vmax);
       if (!X_ROWARRIVE) {
         tmem_st_wait();                    // warp-collective: every lane's re-arm stores have landed
         tc_fence_before();
@@ -676,6 +763,17 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
       }
     }
     G0 += ngrp;
+    if (EPI == EPI_FQ) {                    // one atomic pair per warp and tile (a tile never spans frames)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      }
+      if (lane == 0 && vmin <= vmax) {
+        atomic_min_float(fa.mm + (long long)b * fa.mm_stride, vmin);
+        atomic_max_float(fa.mm + (long long)b * fa.mm_stride + 1, vmax);
+      }
+    }
   }
 }
 
@@ -811,7 +909,7 @@ template <int KS, int NS, int EPI, int RS, int COUT, int OUTM, bool FLOOR, int E
 __global__ void __launch_bounds__((CTRL_WARPS + EPI_WARPS) * 32, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ UmmaParams P,
                  const uint8_t* __restrict__ w_img, const uint4* __restrict__ shortcut, uint4* __restrict__ out,
-                 int8_t* __restrict__ q5, float* __restrict__ y) {
+                 int8_t* __restrict__ q5, float* __restrict__ y, const __grid_constant__ FqArgs fa) {
   constexpr int NCOLS = 16 * NS;
   constexpr int NSLOT = TMEM_COLS / NCOLS;
 
@@ -899,7 +997,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     // ================= epilogue =================
     constexpr bool PIN = !X_NOPIN && NS == 1 && (EPI == EPI_PLAIN || (EPI == EPI_FINAL && OUTM != 0));
     epilogue_warps<NS, EPI, RS, COUT, OUTM, FLOOR, EPI_WARPS, PIN>(P, warp - CTRL_WARPS, lane, tmem_base, acc_full, acc_empty,
-                                                                   shortcut, out, q5, y);
+                                                                   shortcut, out, q5, y, fa);
   }
 
   // ---- teardown ----
@@ -1061,8 +1159,9 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     }
   } else if (warp < CTRL_WARPS + EPI_WARPS) {
     // ================= epilogue (shared with the 16-channel kernel, EPI_PLAIN) =================
+    const FqArgs no_fq{};
     epilogue_warps<NS, EPI_PLAIN, 1, 0, 0, FLOOR, EPI_WARPS, false>(P, warp - CTRL_WARPS, lane, tmem_base, acc_full, acc_empty, nullptr,
-                                                                    out, nullptr, nullptr);
+                                                                    out, nullptr, nullptr, no_fq);
   } else {
     // ================= builders =================
     const int bt = threadIdx.x - (CTRL_WARPS + EPI_WARPS) * 32;       // 0 .. 255
@@ -1423,12 +1522,13 @@ int umma_prepare_layer(LayerDev& L, const int8_t* w) {
 
 template <int KS, int NS, int EPI, int RS, int COUT, int OUTM, bool FLOOR, int EPI_WARPS>
 static int launch_one(const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L, const uint8_t* d_shortcut,
-                      uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem, cudaStream_t st) {
+                      uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem, cudaStream_t st,
+                      const FqArgs& fa = FqArgs{}) {
   auto kern = conv_umma_kernel<KS, NS, EPI, RS, COUT, OUTM, FLOOR, EPI_WARPS>;
   static std::atomic<uint64_t> optin_done{0};
   if (int rc = ensure_smem_optin(kern, 227 * 1024, optin_done)) return rc;
   kern<<<grid, (CTRL_WARPS + EPI_WARPS) * 32, smem, st>>>(tmap, P, L.d_wumma, reinterpret_cast<const uint4*>(d_shortcut),
-                                                          reinterpret_cast<uint4*>(d_out), d_q5, d_y);
+                                                          reinterpret_cast<uint4*>(d_out), d_q5, d_y, fa);
   SESRQ_LAUNCH_CHECK("conv_umma_kernel");
   return SESRQ_OK;
 }
@@ -1639,10 +1739,10 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
 #undef SESRQ_L0_CASE
 }
 
-int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, const uint8_t* d_shortcut,
-                     uint8_t* d_out, int8_t* d_q5, float* d_y, int B, int H, int W, cudaStream_t st) {
+// Tiling, tensor map and kernel parameters of one 16-channel-layout launch (shared by the integer and fake-quant paths).
+static int plan_conv_launch(const LayerDev& L, const uint8_t* d_in, int B, int H, int W, UmmaParams& P, CUtensorMap& tmap,
+                            int& grid, size_t& smem) {
   const LayerConst& c = L.c;
-  if (is_l0_layout(c)) return launch_conv_umma_l0(L, d_x, d_out, B, H, W, st);
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return SESRQ_EUNSUPPORTED;
   if (!d_in) return SESRQ_EINVAL;
@@ -1651,7 +1751,6 @@ int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, c
   const int N = L.umma_n;
 
   // ---- tiling: 128-pixel pitch (one TMA box row = 2048 B), TH output rows per tile ----
-  UmmaParams P;
   memset(&P, 0, sizeof(P));
   P.tiles_x = cdiv(W, UMMA_M - 2 * pad);
   P.TW = cdiv(W, P.tiles_x);
@@ -1659,7 +1758,6 @@ int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, c
   const uint32_t w_bytes = (uint32_t)pairs * 2 * c.k * N * 16;
   const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (2 * MAX_STAGES + 2 * (TMEM_COLS / N)) + 64 + 1024;
   const int sms = sm_count();
-  // slack: the last row's rightmost K chunk reaches 2*pad + 1 pixels past the row
   // slack: the last row's rightmost K chunk reaches 2*pad + 1 pixels past the row
   // measured: 16-channel layers are fastest with 2 bands (TH = 16: the 32-slot ring then holds two tiles; 1080p x2 3x3
   // 0.178 vs 0.185 ms with 3 bands); the 16-output x4 final layer with 3 (540x960: 0.909 vs 0.955 ms)
@@ -1683,7 +1781,6 @@ int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, c
   P.dbg = tuning().dbg;
 
   // ---- tensor map over the NHWC16 input viewed as (W*2 x 8-byte, H, B) ----
-  CUtensorMap tmap;
   cuuint64_t gdim[3] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t gstr[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
   cuuint32_t box[3] = {(cuuint32_t)UMMA_M * 2, (cuuint32_t)(P.TH + 2 * pad), 1};
@@ -1695,11 +1792,39 @@ int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, c
     set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
     return SESRQ_ECUDA;
   }
+  grid = std::min(P.num_tiles, sms);
+  smem = (size_t)P.stage_bytes * P.stages + fixed;
+  return SESRQ_OK;
+}
 
-  const int grid = std::min(P.num_tiles, sms);
-  const size_t smem = (size_t)P.stage_bytes * P.stages + fixed;
+int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, const uint8_t* d_shortcut,
+                     uint8_t* d_out, int8_t* d_q5, float* d_y, int B, int H, int W, cudaStream_t st) {
+  const LayerConst& c = L.c;
+  if (is_l0_layout(c)) return launch_conv_umma_l0(L, d_x, d_out, B, H, W, st);
+  UmmaParams P;
+  CUtensorMap tmap;
+  int grid = 0;
+  size_t smem = 0;
+  if (int rc = plan_conv_launch(L, d_in, B, H, W, P, tmap, grid, smem)) return rc;
+  const int ns = L.umma_n / 16;
   if (c.k == 3) return launch_ns<3>(ns, c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
   return launch_ns<5>(ns, c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+}
+
+// exe_mode 0: four PE-masked accumulator sets (the float-domain PE sums are rounded separately, quan_func.py:333,:386),
+// slots pre-armed with MAGIC_BITS (no integer constants: bias and clamps live in the float domain), fp32 output.
+int launch_conv_umma_fq(const LayerDev& L, const uint8_t* d_in, const FqArgs& fa, int B, int H, int W, cudaStream_t st) {
+  const LayerConst& c = L.c;
+  if (c.epi != EPI_FQ || L.umma_n != 64 || !fa.fp || !fa.xout || !fa.mm || !fa.tapsum) return SESRQ_EINVAL;
+  UmmaParams P;
+  CUtensorMap tmap;
+  int grid = 0;
+  size_t smem = 0;
+  if (int rc = plan_conv_launch(L, d_in, B, H, W, P, tmap, grid, smem)) return rc;
+  for (int p = 0; p < 4; ++p)
+    for (int n = 0; n < 16; ++n) P.c_init[p][n] = MAGIC_BITS;
+  if (c.k == 3) return launch_one<3, 4, EPI_FQ, 1, 0, 0, false, 8>(tmap, P, L, nullptr, nullptr, nullptr, nullptr, grid, smem, st, fa);
+  return launch_one<5, 4, EPI_FQ, 1, 0, 0, false, 8>(tmap, P, L, nullptr, nullptr, nullptr, nullptr, grid, smem, st, fa);
 }
 
 }  // namespace sesrq

@@ -2,8 +2,9 @@
 
 Per frame, every activation domain is quantised with THAT frame's min/max (quan_func.py:177-207); the
 running min/max over all frames is what the calibration tail (test.py:186-217) turns into thresholds.
-The observer state (running min/max, optional 2048-bin histograms for the KL calibrator) stays on the
-device; nothing is synchronised per frame unless the caller asks for the numbers.
+A batch is ONE C call (sesrq_fq_forward_batch: frames are a batch dimension of every kernel, each frame keeps
+its own ranges).  The observer state (running min/max, per-frame min/max of the last call, optional 2048-bin
+histograms for the KL calibrator) stays on the device; nothing is synchronised unless the caller asks.
 """
 from __future__ import annotations
 
@@ -78,7 +79,7 @@ class FakeQuantNet:
         mm[:, 0] = float("inf")
         mm[:, 1] = float("-inf")
         self.minmax = mm.to(self.device)                    # running (min, max) per domain, on device
-        self.frame_minmax = torch.zeros_like(self.minmax)
+        self.frame_minmax = torch.zeros((1, _lib.NUM_DOMAINS, 2), dtype=torch.float32, device=self.device)
 
     def enable_histograms(self, ranges: Sequence[Sequence[float]]):
         """Second calibration pass: accumulate 2048-bin histograms of every domain over [lo, hi]."""
@@ -98,22 +99,26 @@ class FakeQuantNet:
         return (1, self.cout // (self.r * self.r), H * self.r, W * self.r)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x: float32 CUDA [B, Cin, H, W]; frames are processed one by one (per-frame dynamic ranges)."""
+        """x: float32 CUDA [B, Cin, H, W]; all frames in one call, every frame with its own dynamic ranges.
+        self.frame_minmax: float32 [B, 6, 2] of this call."""
         if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != self.cin:
             raise _lib.SesrqError("FakeQuantNet.forward needs a float32 CUDA [B,%d,H,W] tensor" % self.cin)
         x = x.contiguous()
         B, _, H, W = x.shape
         y = torch.empty((B,) + self.out_shape(H, W)[1:], dtype=torch.float32, device=x.device)
-        need = int(self.lib.sesrq_fq_ws_bytes(self._h, H, W))
+        self.frame_minmax = torch.empty((B, _lib.NUM_DOMAINS, 2), dtype=torch.float32, device=x.device)
+        if B == 0:
+            return y
+        need = int(self.lib.sesrq_fq_ws_bytes_batch(self._h, B, H, W))
         if self._ws is None or self._ws.numel() < need:
+            self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
         with torch.cuda.device(x.device):
-            for b in range(B):
-                rc = self.lib.sesrq_fq_forward(self._h, _ptr(x[b]), H, W, _ptr(y[b]), _ptr(self.minmax),
-                                               _ptr(self.frame_minmax), _ptr(self.hist), _ptr(self.hist_range),
-                                               _ptr(self._ws), self._ws.numel(), st)
-                _lib.check(rc, "sesrq_fq_forward")
+            rc = self.lib.sesrq_fq_forward_batch(self._h, _ptr(x), B, H, W, _ptr(y), _ptr(self.minmax),
+                                                 _ptr(self.frame_minmax), _ptr(self.hist), _ptr(self.hist_range),
+                                                 _ptr(self._ws), self._ws.numel(), st)
+        _lib.check(rc, "sesrq_fq_forward_batch")
         return y
 
     __call__ = forward

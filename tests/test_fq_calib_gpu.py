@@ -33,7 +33,7 @@ def test_fq_forward_vs_oracle_and_reference(case):
     net = make_fq(g)
     y = net(torch.from_numpy(g.x).cuda()).cpu().numpy()
     y_o, mins_o, maxs_o = fo.forward_fq(g.wf, g.bf, g.x, g.r, observe_out=(int(g["mflag"]) == 3), pe_add_bit=g.pe_add_bit)
-    mm = net.frame_minmax.cpu().numpy()
+    mm = net.frame_minmax.cpu().numpy()[0]
     # same integer-exact formulation as the oracle: identical per-domain ranges and output
     assert np.array_equal(mm[:, 0], np.array(mins_o, dtype=np.float32))
     assert np.array_equal(mm[:, 1], np.array(maxs_o, dtype=np.float32))
@@ -43,6 +43,28 @@ def test_fq_forward_vs_oracle_and_reference(case):
     s5 = (g["fq_maxs"][5] - g["fq_mins"][5]) / 255
     assert mse == 0 or 10 * np.log10(1.0 / mse) >= 60.0
     assert float(np.abs(y - ref).max()) <= 8 * s5
+
+
+def test_fq_batch_frames_with_unusual_ranges():
+    """Frames whose minimum is far from code 0 (operand offset dmin != 0: zero padding is then not byte 0), a signed
+    frame and a tiny-range frame, batched with ordinary ones: every frame must equal the oracle's single-frame result,
+    and the per-frame ranges are reported per frame."""
+    g = load_golden("x2_small")
+    net = make_fq(g)
+    gen = torch.Generator().manual_seed(21)
+    base = torch.rand(5, 3, 19, 23, generator=gen)
+    x = base.clone()
+    x[1] = base[1] * 0.05 + 0.9            # [0.9, 0.95]: min / s ~ 4600 -> large positive dmin
+    x[2] = base[2] * 2 - 1                 # signed input: negative dmin (z0 > -128)
+    x[3] = base[3] * 1e-3 + 0.25
+    y = net(x.cuda()).cpu().numpy()
+    fm = net.frame_minmax.cpu().numpy()
+    assert fm.shape == (5, 6, 2)
+    for b in range(5):
+        y_o, mins_o, maxs_o = fo.forward_fq(g.wf, g.bf, x[b:b + 1].numpy(), g.r)
+        assert np.array_equal(fm[b, :, 0], np.array(mins_o, dtype=np.float32)), "frame %d mins" % b
+        assert np.array_equal(fm[b, :, 1], np.array(maxs_o, dtype=np.float32)), "frame %d maxs" % b
+        assert np.array_equal(y[b:b + 1], y_o), "frame %d" % b
 
 
 def test_fq_batch_is_frame_by_frame_and_running_minmax():
