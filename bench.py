@@ -503,6 +503,33 @@ def main():
             del wx, wq5, wy_, wnet
             torch.cuda.empty_cache()
 
+    # ---- BASELINE config 1: one 80x960 frame, launch-latency bound -> eager launches vs one CUDA-graph replay ----
+    small = None
+    if world == 1 and not args.no_workloads and not args.batch:
+        sg = load_case("x2_fixture")
+        snet = Int8Net(compile_network([torch.from_numpy(w) for w in sg.wf], [torch.from_numpy(b) for b in sg.bf], sg.scales,
+                                       sg.zeros, sg.r), device=dev)
+        sx = torch.from_numpy(sg.x).to(dev)
+        sq, sy = snet.out_shapes(1, 80, 960)
+        sy_t = torch.empty(sy, dtype=torch.float32, device=dev)
+        eager_ms = time_net(snet, sx, False, True, None, sy_t, 200)
+        gnet = snet.capture(sx, want_q5=False, want_y=True)
+        for _ in range(5):
+            gnet()
+        torch.cuda.synchronize(dev)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(200):
+            gnet()
+        g1.record()
+        torch.cuda.synchronize(dev)
+        graph_ms = g0.elapsed_time(g1) / 200
+        same = bool(torch.equal(gnet.y, sy_t))
+        small = {"workload": "sesr_x2_int8_sim_80x960, 1 frame (BASELINE config 1), y only", "eager_us_per_frame": eager_ms * 1e3,
+                 "cuda_graph_us_per_frame": graph_ms * 1e3, "graph_equals_eager": same,
+                 "note": "back-to-back frames on one stream; 5 kernels per frame, 40 tiles on 148 SMs"}
+        snet.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         secs, thr = cpu_reference_time(case, H, W, 1, 2)
@@ -523,7 +550,7 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args.workload, case, B, H, W, r, cin, cout, args.outputs, world, B * cin * H * W * 4 / 1e6),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "calibration": calib, "output_variants": single, "workloads": workloads,
+            "cpu_baseline": cpu, "calibration": calib, "output_variants": single, "workloads": workloads, "small_frame": small,
             "stack": {"alg_bytes_per_lr_px": sum(lbytes), "achieved_gbs": stack_gbs, "frac_of_hbm_peak": stack_gbs / peak,
                       "int8_tops": 2 * total_macs * B * H * W / (ms_step * 1e-3) / 1e12, "us_per_frame": ms_step * 1e3 / B},
             "layers": per_layer,

@@ -8,8 +8,8 @@ The directory of this package is also the drop-in import root for the reference'
 from ._lib import SesrqError, load_library, IMPL_AUTO, IMPL_GENERIC, IMPL_UMMA  # noqa: F401
 from .compile import (CompiledLayer, CompiledNet, compile_network, collapsed_convs,  # noqa: F401
                       quan_layer_between_const, thresholds_from_minmax)
-from .net import Int8Net  # noqa: F401
+from .net import GraphedInt8Net, Int8Net  # noqa: F401
 
 __all__ = ["SesrqError", "load_library", "IMPL_AUTO", "IMPL_GENERIC", "IMPL_UMMA", "CompiledLayer",
            "CompiledNet", "compile_network", "collapsed_convs", "quan_layer_between_const",
-           "thresholds_from_minmax", "Int8Net"]
+           "thresholds_from_minmax", "Int8Net", "GraphedInt8Net"]

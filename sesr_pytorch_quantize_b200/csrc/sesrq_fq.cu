@@ -113,14 +113,15 @@ __global__ void fqb_params_kernel(const float* __restrict__ mm, int dom, int B, 
 
 // operand bytes b = q + 128 in the PE-major byte order (byte j <-> channel (j & 3) * 4 + (j >> 2)), q from THIS frame's
 // scale / zero (:207).  NCHW input (layer 0) and NHWC16 input (layers 1..4).
-__global__ void __launch_bounds__(256) fqb_quant_nchw_kernel(const float* __restrict__ x, int C, int HW, long long npix,
-                                                             const FqFrameParams* __restrict__ fp, uint4* __restrict__ act) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npix) return;
-  const long long f = i / HW;
-  const int p = (int)(i - f * HW);
+__global__ void __launch_bounds__(256) fqb_quant_nchw_kernel(const float* __restrict__ x, int C, int HW,
+                                                             const FqFrameParams* __restrict__ fp, uint4* __restrict__ act_all) {
+  const int f = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
   const float sf = fp[f].in_s, zf = fp[f].in_z;
-  const float* xb = x + f * (long long)C * HW + p;
+  const float* xb = x + (size_t)f * C * HW + p;
+  uint4* act = act_all + (size_t)f * HW;
+  const int i = p;
   uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
   for (int c = 0; c < SESRQ_MAX_CH; ++c) {
@@ -133,31 +134,40 @@ __global__ void __launch_bounds__(256) fqb_quant_nchw_kernel(const float* __rest
   act[i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__global__ void __launch_bounds__(256) fqb_quant_nhwc_kernel(const float4* __restrict__ x, int HW, long long npix,
-                                                             const FqFrameParams* __restrict__ fp, uint4* __restrict__ act) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npix) return;
-  const long long f = i / HW;
-  const float sf = fp[f].in_s, zf = fp[f].in_z;
-  float v[16];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 t = __ldg(x + 4 * i + q);
-    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+// NHWC16 fp32 -> operand bytes, 4 lanes per pixel: lane q reads the float4 of channels 4q .. 4q + 3 (consecutive lanes
+// read consecutive 16 B), quantises them, and a 4 x 4 byte transpose across the four lanes (two shuffles) leaves lane q
+// with word q of the pixel's uint4 -- PE-major byte order: word e, byte q  <->  channel 4q + e.
+__global__ void __launch_bounds__(256) fqb_quant_nhwc_kernel(const float4* __restrict__ x4, int HW,
+                                                             const FqFrameParams* __restrict__ fp, uint32_t* __restrict__ act4) {
+  const int f = blockIdx.y;                                                    // grid.y = frame: no per-thread division
+  const unsigned tf = blockIdx.x * blockDim.x + threadIdx.x;                   // one float4 each; whole warps stay together
+  const bool live = tf < (unsigned)HW * 4u;
+  const float4* x = x4 + (size_t)f * HW * 4;
+  uint32_t* act = act4 + (size_t)f * HW * 4;
+  const unsigned t = tf;
+  uint32_t w = 0u;
+  if (live) {
+    const float sf = fp[f].in_s, zf = fp[f].in_z;
+    const float4 v = __ldg(x + t);
+    const uint32_t b0 = (uint32_t)(quant_add_zero(__fdiv_rn(v.x, sf), zf) + 128);
+    const uint32_t b1 = (uint32_t)(quant_add_zero(__fdiv_rn(v.y, sf), zf) + 128);
+    const uint32_t b2 = (uint32_t)(quant_add_zero(__fdiv_rn(v.z, sf), zf) + 128);
+    const uint32_t b3 = (uint32_t)(quant_add_zero(__fdiv_rn(v.w, sf), zf) + 128);
+    w = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);                              // byte e = this lane's contribution to word e
   }
-  uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const int q = quant_add_zero(__fdiv_rn(v[c], sf), zf);
-    const int j = (c & 3) * 4 + (c >> 2);
-    w[j >> 2] |= (uint32_t)(q + 128) << (8 * (j & 3));
-  }
-  act[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  // transpose: lane q ends with (lane0.byte q, lane1.byte q, lane2.byte q, lane3.byte q)
+  const int q = threadIdx.x & 3;
+  uint32_t p1 = __shfl_xor_sync(0xffffffffu, w, 1);
+  w = (q & 1) ? __byte_perm(p1, w, 0x7351) : __byte_perm(w, p1, 0x6240);      // odd: (p.b1, own.b1, p.b3, own.b3); even: (own.b0, p.b0, own.b2, p.b2)
+  uint32_t p2 = __shfl_xor_sync(0xffffffffu, w, 2);
+  w = (q & 2) ? __byte_perm(p2, w, 0x7632) : __byte_perm(w, p2, 0x5410);      // upper pair: (p.h1, own.h1); lower pair: (own.h0, p.h0)
+  if (live) act[t] = w;
 }
 
-// 2048-bin histogram of the first `nch` channels of an NHWC16 fp32 tensor over a fixed range (KL pass 2); per-CTA
-// shared bins, warp-aggregated atomics (ReLU outputs pile up in bin 0)
-__global__ void __launch_bounds__(256) fqb_hist_nhwc_kernel(const float* __restrict__ x, size_t n, int nch,
+// 2048-bin histogram of the first `nch` channels of an NHWC16 fp32 tensor over a fixed range (KL pass 2).  Per-CTA
+// shared bins; float4 loads; ReLU outputs pile up in bin 0, which would serialise the shared atomics, so bin 0 is
+// counted in a register and added once per warp.
+__global__ void __launch_bounds__(256) fqb_hist_nhwc_kernel(const float4* __restrict__ x, size_t n4, int nch,
                                                             const float* __restrict__ d_range,
                                                             unsigned long long* __restrict__ hist) {
   __shared__ unsigned int s_hist[SESRQ_KL_BINS];
@@ -166,19 +176,26 @@ __global__ void __launch_bounds__(256) fqb_hist_nhwc_kernel(const float* __restr
   for (int i = threadIdx.x; i < SESRQ_KL_BINS; i += blockDim.x) s_hist[i] = 0u;
   __syncthreads();
   const float scale = __fdiv_rn((float)SESRQ_KL_BINS, __fsub_rn(hi, lo));
-  const size_t n_round = ((n + 31) / 32) * 32;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (size_t)gridDim.x * blockDim.x) {
-    const bool valid = i < n && (int)(i & 15) < nch;
-    const float v = valid ? __ldg(x + i) : 0.f;
-    const float c = fminf(fmaxf(v, lo), hi);
-    int b = (int)floorf(__fmul_rn(__fsub_rn(c, lo), scale));
-    b = min(max(b, 0), SESRQ_KL_BINS - 1);
-    const unsigned active = __ballot_sync(0xffffffffu, valid);
-    if (valid) {
-      const unsigned peers = __match_any_sync(active, b);
-      if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(s_hist + b, __popc(peers));
+  unsigned int zeros = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i & 3) * 4;                       // first channel of this float4
+    if (c0 >= nch) continue;
+    const float4 v4 = __ldg(x + i);
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (c0 + e < nch) {
+        const float c = fminf(fmaxf(v[e], lo), hi);
+        int b = (int)floorf(__fmul_rn(__fsub_rn(c, lo), scale));
+        b = min(max(b, 0), SESRQ_KL_BINS - 1);
+        if (b == 0) ++zeros;
+        else atomicAdd(s_hist + b, 1u);
+      }
     }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+  if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(s_hist, zeros);
   __syncthreads();
   for (int i = threadIdx.x; i < SESRQ_KL_BINS; i += blockDim.x) {
     const unsigned int c = s_hist[i];
@@ -187,34 +204,45 @@ __global__ void __launch_bounds__(256) fqb_hist_nhwc_kernel(const float* __restr
 }
 
 // domain-5 fake-quant with the frame's range (test.py:90-91 maps PixelShuffle to the quantiser; :207-215) + PixelShuffle:
-// X_5 fp32 NHWC16 -> y fp32 NCHW [B, C / r^2, rH, rW]
-__global__ void __launch_bounds__(256) fqb_final_kernel(const float4* __restrict__ x5, int C, int H, int W, int r, long long npix,
+// X_5 fp32 NHWC16 -> y fp32 NCHW [B, C / r^2, rH, rW].  4 lanes per pixel (lane q: channels 4q .. 4q + 3, one coalesced
+// float4 load); for r = 2 / 4 the lane's channels are 2 x 2 / 1 x 4 neighbouring output pixels -> vector stores.
+__global__ void __launch_bounds__(256) fqb_final_kernel(const float4* __restrict__ x5, int C, int H, int W, int r,
                                                         int do_quant, const FqFrameParams* __restrict__ fp, float* __restrict__ y) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npix) return;
+  const int f = blockIdx.y;
   const int HW = H * W;
-  const long long f = i / HW;
-  const int p = (int)(i - f * HW);
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = (int)(t >> 2);
+  const int q = (int)(t & 3);
+  if (p >= HW || 4 * q >= C) return;
   const int yy = p / W, xx = p - yy * W;
-  const float sf = fp[f].in_s, zf = fp[f].in_z;
-  float v[16];
+  const float4 v4 = __ldg(x5 + (size_t)f * HW * 4 + t);
+  float v[4] = {v4.x, v4.y, v4.z, v4.w};
+  if (do_quant) {
+    const float sf = fp[f].in_s, zf = fp[f].in_z;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 t = __ldg(x5 + 4 * i + q);
-    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    for (int e = 0; e < 4; ++e) {
+      const float qv = (float)quant_add_zero(__fdiv_rn(v[e], sf), zf);
+      v[e] = __fmul_rn(__fsub_rn(qv, zf), sf);                    // :215
+    }
   }
-  const int r2 = r * r;
-  float* yb = y + f * (long long)C * HW;
+  float* yb = y + (size_t)f * C * HW;
+  const size_t Wr = (size_t)W * r;
+  if (r == 2) {                                                    // channels 4q .. 4q + 3 = plane q, rows 2yy, 2yy + 1, columns 2xx, 2xx + 1
+    float* d = yb + ((size_t)q * (H * 2) + 2 * yy) * Wr + 2 * xx;
+    *reinterpret_cast<float2*>(d) = make_float2(v[0], v[1]);
+    *reinterpret_cast<float2*>(d + Wr) = make_float2(v[2], v[3]);
+  } else if (r == 4) {                                             // plane q / 4, row 4yy + q % 4, columns 4xx .. 4xx + 3
+    float* d = yb + ((size_t)(q >> 2) * (H * 4) + 4 * yy + (q & 3)) * Wr + 4 * xx;
+    *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    const int r2 = r * r;
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    if (c < C) {
-      float o = v[c];
-      if (do_quant) {
-        const float q = (float)quant_add_zero(__fdiv_rn(o, sf), zf);
-        o = __fmul_rn(__fsub_rn(q, zf), sf);                      // :215
+    for (int e = 0; e < 4; ++e) {
+      const int c = 4 * q + e;
+      if (c < C) {
+        const int cc = c / r2, ii = (c % r2) / r, jj = c % r;
+        yb[((size_t)cc * (H * r) + (yy * r + ii)) * Wr + (xx * r + jj)] = v[e];
       }
-      const int cc = c / r2, ii = (c % r2) / r, jj = c % r;
-      yb[((size_t)cc * (H * r) + (yy * r + ii)) * (size_t)(W * r) + (xx * r + jj)] = o;
     }
   }
 }
@@ -387,7 +415,6 @@ int sesrq_fq_forward_batch(const SesrqFq* fq, const float* d_x, int B, int H, in
     const int nb = std::min(p.chunk, B - b0);
     const float* x = d_x + (size_t)b0 * cin * HW;
     const long long npix = (long long)nb * HW;
-    const unsigned pgrid = (unsigned)((npix + 255) / 256);
     fqb_init_mm_kernel<<<(nb * MM_STRIDE + 255) / 256, 256, 0, st>>>(mm, nb * MM_STRIDE);
     SESRQ_LAUNCH_CHECK("fqb_init_mm_kernel");
     {
@@ -409,17 +436,19 @@ int sesrq_fq_forward_batch(const SesrqFq* fq, const float* d_x, int B, int H, in
           int rc = launch_hist_dev(x, (size_t)nb * cin * HW, d_hist_range, d_hist, st);
           if (rc) return rc;
         }
-        fqb_quant_nchw_kernel<<<pgrid, 256, 0, st>>>(x, cin, HW, npix, fp, reinterpret_cast<uint4*>(act));
+        fqb_quant_nchw_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)nb), 256, 0, st>>>(x, cin, HW, fp,
+                                                                                                reinterpret_cast<uint4*>(act));
         SESRQ_LAUNCH_CHECK("fqb_quant_nchw_kernel");
       } else {
         if (d_hist) {
-          const size_t n = (size_t)npix * 16;
-          const unsigned hg = (unsigned)std::min<size_t>(std::max<size_t>((n + 4095) / 4096, 1), 148 * 4);
-          fqb_hist_nhwc_kernel<<<hg, 256, 0, st>>>(in_t[i], n, L.c.cin, d_hist_range + 2 * i, d_hist + (size_t)i * SESRQ_KL_BINS);
+          const size_t n4 = (size_t)npix * 4;
+          const unsigned hg = (unsigned)std::min<size_t>(std::max<size_t>((n4 + 2047) / 2048, 1), 148 * 8);
+          fqb_hist_nhwc_kernel<<<hg, 256, 0, st>>>(reinterpret_cast<const float4*>(in_t[i]), n4, L.c.cin, d_hist_range + 2 * i,
+                                                   d_hist + (size_t)i * SESRQ_KL_BINS);
           SESRQ_LAUNCH_CHECK("fqb_hist_nhwc_kernel");
         }
-        fqb_quant_nhwc_kernel<<<pgrid, 256, 0, st>>>(reinterpret_cast<const float4*>(in_t[i]), HW, npix, fp,
-                                                     reinterpret_cast<uint4*>(act));
+        fqb_quant_nhwc_kernel<<<dim3((unsigned)((HW * 4 + 255) / 256), (unsigned)nb), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(in_t[i]), HW, fp, reinterpret_cast<uint32_t*>(act));
         SESRQ_LAUNCH_CHECK("fqb_quant_nhwc_kernel");
       }
       FqArgs fa{};
@@ -435,17 +464,18 @@ int sesrq_fq_forward_batch(const SesrqFq* fq, const float* d_x, int B, int H, in
       if (rc) return rc;
     }
     if (d_hist) {
-      const size_t n = (size_t)npix * 16;
-      const unsigned hg = (unsigned)std::min<size_t>(std::max<size_t>((n + 4095) / 4096, 1), 148 * 4);
-      fqb_hist_nhwc_kernel<<<hg, 256, 0, st>>>(X[2], n, cout, d_hist_range + 10, d_hist + (size_t)5 * SESRQ_KL_BINS);
+      const size_t n4 = (size_t)npix * 4;
+      const unsigned hg = (unsigned)std::min<size_t>(std::max<size_t>((n4 + 2047) / 2048, 1), 148 * 8);
+      fqb_hist_nhwc_kernel<<<hg, 256, 0, st>>>(reinterpret_cast<const float4*>(X[2]), n4, cout, d_hist_range + 10,
+                                               d_hist + (size_t)5 * SESRQ_KL_BINS);
       SESRQ_LAUNCH_CHECK("fqb_hist_nhwc_kernel");
     }
     // SESR: the PixelShuffle input is fake-quantised with this frame's range (test.py:90-91);
     // NRDM (observe_out): no PixelShuffle node, the conv output is only observed (quan_func.py:460-479)
     fqb_params_kernel<<<(nb + 127) / 128, 128, 0, st>>>(mm, 5, nb, 1.0, fq->d_bias[4], 0, D.pe_acc_bits, D.pe_add_bits, 0.0, 0.0, fp);
     SESRQ_LAUNCH_CHECK("fqb_params_kernel");
-    fqb_final_kernel<<<pgrid, 256, 0, st>>>(reinterpret_cast<const float4*>(X[2]), cout, H, W, D.r_shuffle, npix,
-                                            D.observe_out ? 0 : 1, fp, d_y + (size_t)b0 * y_frame);
+    fqb_final_kernel<<<dim3((unsigned)((HW * 4 + 255) / 256), (unsigned)nb), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(X[2]), cout, H, W, D.r_shuffle, D.observe_out ? 0 : 1, fp, d_y + (size_t)b0 * y_frame);
     SESRQ_LAUNCH_CHECK("fqb_final_kernel");
     fqb_commit_kernel<<<1, 32, 0, st>>>(mm, nb, d_minmax, d_frame_minmax ? d_frame_minmax + (size_t)b0 * MM_STRIDE : nullptr);
     SESRQ_LAUNCH_CHECK("fqb_commit_kernel");

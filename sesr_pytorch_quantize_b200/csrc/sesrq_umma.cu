@@ -164,6 +164,11 @@ __device__ __forceinline__ float2 f2_fma3(float2 a, float2 b, float2 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)), "l"(f2_pack(c.x, c.y)));
   return f2_unpack(r);
 }
+__device__ __forceinline__ float2 f2_add2(float2 a, float2 b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)));
+  return f2_unpack(r);
+}
 __device__ __forceinline__ float2 f2_add(float2 a, float b) {
   uint64_t r;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b, b)));
@@ -272,6 +277,8 @@ struct UmmaParams {
   int32_t B, H, W, TH, TW, tiles_x, tiles_y, num_tiles, pad;
   uint32_t box_bytes, stage_bytes, w_bytes;
   int32_t stages;                        // tile buffers in flight (2..MAX_STAGES)
+  int32_t sc_stages;                     // EPI_RESIDUAL: shortcut tile buffers staged by TMA (0 = the epilogue reads global memory)
+  uint32_t sc_stage_bytes;               //   one buffer: TH rows x 128 pixels x 16 B
   int32_t nbw;                           // issuer warps = row bands per tile (1..3)
   uint32_t idesc;
   // layer-0 kernel only
@@ -545,29 +552,22 @@ __device__ __forceinline__ void slot_fence(int (&a)[NS][16]) {
 //   SLOW: per-frame operand offset dmin != 0 (the frame's minimum is not code 0: zero padding is then NOT byte 0, so the
 //         in-frame tap sums times dmin are added per pixel) and / or clamps that can fire.  Rare, kept out of line.
 // ------------------------------------------------------------------------------------------------
-template <bool SLOW>
-__device__ __forceinline__ void epilogue_pixel_fq(const FqArgs& fa, const FqFrameParams& f, const int (&acc)[4][16],
-                                                  float* __restrict__ xo, const float* __restrict__ xr, const bool valid,
-                                                  const int gy, const int gx, const int H, const int W, const int ks,
-                                                  float& vmin, float& vmax) {
-  float4 res[4];
-  if (xr != nullptr && valid) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) res[q] = __ldg(reinterpret_cast<const float4*>(xr) + q);
-  }
-  float o[16];
-#pragma unroll
+// General form (SLOW): scalar, with the operand-offset correction and the clamps.
+// Out of line, on a COPY of the accumulators in local memory (the caller's stay in registers for the fast form).
+__device__ __noinline__ void epilogue_pixel_fq_slow(const FqArgs& fa, const FqFrameParams& f, const int* acc /*[4][16]*/,
+                                                    float* o /*[16]*/, const int gy, const int gx, const int H, const int W,
+                                                    const int ks) {
+#pragma unroll 1
   for (int n = 0; n < 16; ++n) {
     const int co = chan_of_byte(n);                    // accumulator column n <-> output channel (PE-major byte order)
-    float a[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) a[p] = __fadd_rn(__int_as_float(acc[p][n]), -MAGIC_F);       // exact: A_p as a float
-    if (SLOW && f.dmin != 0) {
-      // d = byte + dmin and out-of-frame d = 0: add dmin * (sum of the PE's weights over the IN-FRAME taps); integer
-      // arithmetic like the oracle's int64 conv, converted to float once
-      const int pad = (ks - 1) / 2;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
+    float s = 0.f;
+#pragma unroll 1
+    for (int p = 0; p < 4; ++p) {
+      float a = __fadd_rn(__int_as_float(acc[p * 16 + n]), -MAGIC_F);                        // exact: A_p as a float
+      if (f.dmin != 0) {
+        // d = byte + dmin and out-of-frame d = 0: add dmin * (sum of the PE's weights over the IN-FRAME taps); integer
+        // arithmetic like the oracle's int64 conv, converted to float once
+        const int pad = (ks - 1) / 2;
         long long corr = 0;
         for (int dy = 0; dy < ks; ++dy) {
           const int sy = gy + dy - pad;
@@ -578,35 +578,99 @@ __device__ __forceinline__ void epilogue_pixel_fq(const FqArgs& fa, const FqFram
             corr += fa.tapsum[(dy * ks + dx) * 64 + p * 16 + n];
           }
         }
-        a[p] = (float)((long long)__float2int_rn(a[p]) + corr * (long long)f.dmin);
+        a = (float)((long long)__float2int_rn(a) + corr * (long long)f.dmin);
       }
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      float yp = __fmul_rn(a[p], f.cscale);
-      if (SLOW) yp = fminf(fmaxf(yp, f.lo_acc), f.hi_acc);                                   // :333
+      float yp = __fmul_rn(a, f.cscale);
+      yp = fminf(fmaxf(yp, f.lo_acc), f.hi_acc);                                             // :333
       s = __fadd_rn(s, yp);                                                                  // :386
     }
-    if (SLOW) s = fminf(fmaxf(s, f.lo_add), f.hi_add);                                       // :434
+    s = fminf(fmaxf(s, f.lo_add), f.hi_add);                                                 // :434
     s = __fadd_rn(s, f.bias[co]);                                                            // :459
     if (fa.relu) s = fmaxf(s, 0.f);
     o[co] = s;
   }
-  if (xr != nullptr) {                                                                       // AddOp (models/sesr.py:45)
+}
+
+// Fast form: no operand offset (dmin == 0).  Channel pairs (columns 2k, 2k + 1 = channels c, c + 4) on packed fp32
+// pairs: exact A_p (FADD2), product (FMUL2), bias (FADD2); every lane is the scalar IEEE operation, so the result is
+// bit-identical to the general form.  CLAMP: the float-domain PE / adder clamps can fire for this frame's operand range
+// (decided per frame by fqb_params_kernel from the layer's weight mass), otherwise they are skipped as provably inert.
+template <bool CLAMP>
+__device__ __forceinline__ void epilogue_pixel_fq_fast(const FqArgs& fa, const FqFrameParams& f, const float2 (&bias2)[8],
+                                                       const int (&acc)[4][16], float (&o)[16]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    // NOTE: the PE sums are scalar adds on purpose.  ptxas contracts `mul.rn.f32x2` feeding `add.rn.f32x2` into one
+    // FFMA2 (seen in the SASS: a single rounding, not the reference's two); the scalar add.rn.f32 is never fused.
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float2 a = f2_add(make_float2(__int_as_float(acc[p][2 * k]), __int_as_float(acc[p][2 * k + 1])), -MAGIC_F);
+      float2 yp = f2_mul(a, f.cscale);
+      if (CLAMP) {
+        yp.x = fminf(fmaxf(yp.x, f.lo_acc), f.hi_acc);                                       // :333
+        yp.y = fminf(fmaxf(yp.y, f.lo_acc), f.hi_acc);
+      }
+      s.x = __fadd_rn(s.x, yp.x);                                                            // :386 (first add: 0 + y_0)
+      s.y = __fadd_rn(s.y, yp.y);
+    }
+    if (CLAMP) {
+      s.x = fminf(fmaxf(s.x, f.lo_add), f.hi_add);                                           // :434
+      s.y = fminf(fmaxf(s.y, f.lo_add), f.hi_add);
+    }
+    s = f2_add2(s, bias2[k]);                                                                // :459
+    if (fa.relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); }
+    o[chan_of_byte(2 * k)] = s.x;
+    o[chan_of_byte(2 * k + 1)] = s.y;
+  }
+}
+
+__device__ __forceinline__ void epilogue_pixel_fq(const FqArgs& fa, const FqFrameParams& f, const float2 (&bias2)[8],
+                                                  const int mode, const int (&acc)[4][16], float* __restrict__ xo,
+                                                  const float* __restrict__ xr, const bool valid, const int gy, const int gx,
+                                                  const int H, const int W, const int ks, float& vmin, float& vmax) {
+  float4 res[4];
+  if (xr != nullptr && valid) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) res[q] = __ldg(reinterpret_cast<const float4*>(xr) + q);
+  }
+  float o[16];
+  if (mode == 2) {                          // operand offset: out of line, on a copy
+    int acc_l[64];
+    float o_l[16];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int n = 0; n < 16; ++n) acc_l[p * 16 + n] = acc[p][n];
+    epilogue_pixel_fq_slow(fa, f, acc_l, o_l, gy, gx, H, W, ks);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = o_l[c];
+  } else if (mode == 1) {
+    epilogue_pixel_fq_fast<true>(fa, f, bias2, acc, o);
+  } else {
+    epilogue_pixel_fq_fast<false>(fa, f, bias2, acc, o);
+  }
+  if (xr != nullptr && valid) {                                                              // AddOp (models/sesr.py:45)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      o[4 * q + 0] = __fadd_rn(o[4 * q + 0], res[q].x);
-      o[4 * q + 1] = __fadd_rn(o[4 * q + 1], res[q].y);
-      o[4 * q + 2] = __fadd_rn(o[4 * q + 2], res[q].z);
-      o[4 * q + 3] = __fadd_rn(o[4 * q + 3], res[q].w);
+      const float2 lo = f2_add2(make_float2(o[4 * q], o[4 * q + 1]), make_float2(res[q].x, res[q].y));
+      const float2 hi = f2_add2(make_float2(o[4 * q + 2], o[4 * q + 3]), make_float2(res[q].z, res[q].w));
+      o[4 * q] = lo.x; o[4 * q + 1] = lo.y; o[4 * q + 2] = hi.x; o[4 * q + 3] = hi.y;
     }
   }
   if (valid) {
+    if (fa.cout == 16) {
+      float lo = o[0], hi = o[0];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      if (c < fa.cout) { vmin = fminf(vmin, o[c]); vmax = fmaxf(vmax, o[c]); }
-      else o[c] = 0.f;
+      for (int c = 1; c < 16; ++c) { lo = fminf(lo, o[c]); hi = fmaxf(hi, o[c]); }           // 3-input FMNMX3 chains
+      vmin = fminf(vmin, lo);
+      vmax = fmaxf(vmax, hi);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        if (c < fa.cout) { vmin = fminf(vmin, o[c]); vmax = fmaxf(vmax, o[c]); }
+        else o[c] = 0.f;
+      }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -624,14 +688,20 @@ __device__ __forceinline__ void epilogue_group(const UmmaParams& P, const int cn
                                                int8_t* __restrict__ qb, float* __restrict__ yb, const long long HW,
                                                const float relu_floor, const bool valid, uint64_t* empty_bar, const int lane,
                                                const int wg, const FqArgs& fa, const FqFrameParams& fq, const long long fq_px,
-                                               const int gy0, const int gx, float& vmin, float& vmax) {
+                                               const int gy0, const int gx, float& vmin, float& vmax,
+                                               const uint4* __restrict__ sc_smem, const float2 (&fq_bias2)[8], const int fq_slow) {
   constexpr int NCOLS = 16 * NS;
   constexpr int RG = GroupRows<NS>::value;
   uint4 sc[RG];
 #pragma unroll
   for (int i = 0; i < RG; ++i) {
     sc[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (EPI == EPI_RESIDUAL && valid && i < cnt) sc[i] = __ldg(sc_row + (long long)i * P.W);
+    if (EPI == EPI_RESIDUAL) {
+      // TMA-staged tile (row pitch 128 pixels; out-of-frame pixels are zero-filled and their results never stored),
+      // else straight from global memory
+      if (sc_smem) sc[i] = sc_smem[i * UMMA_M];
+      else if (valid && i < cnt) sc[i] = __ldg(sc_row + (long long)i * P.W);
+    }
   }
   constexpr bool PIPE = !(X_NOPIPE && EPI == EPI_FINAL);
   constexpr bool BRANCH = X_BRANCH && EPI == EPI_FINAL;
@@ -650,9 +720,8 @@ __device__ __forceinline__ void epilogue_group(const UmmaParams& P, const int cn
     if (SESRQ_X_ROWSYNC == 2 || (SESRQ_X_ROWSYNC == 1 && EPI == EPI_FINAL)) asm volatile("bar.sync %0, 128;" ::"r"(2 + wg) : "memory");
     if constexpr (EPI == EPI_FQ && NS == 4) {
       const long long px = fq_px + (long long)i * P.W;
-      const bool slow = (fq.dmin != 0) || fq.clamp_acc || fq.clamp_add;              // per frame: warp-uniform
-      if (slow) epilogue_pixel_fq<true>(fa, fq, acc[cur], fa.xout + px * 16, fa.xres ? fa.xres + px * 16 : nullptr, v_i, gy0 + i, gx, P.H, P.W, 2 * P.pad + 1, vmin, vmax);
-      else epilogue_pixel_fq<false>(fa, fq, acc[cur], fa.xout + px * 16, fa.xres ? fa.xres + px * 16 : nullptr, v_i, gy0 + i, gx, P.H, P.W, 2 * P.pad + 1, vmin, vmax);
+      epilogue_pixel_fq(fa, fq, fq_bias2, fq_slow, acc[cur], fa.xout + px * 16, fa.xres ? fa.xres + px * 16 : nullptr, v_i, gy0 + i,
+                        gx, P.H, P.W, 2 * P.pad + 1, vmin, vmax);
     } else if (BRANCH) {
       if (v_i) epilogue_pixel<NS, EPI, RS, COUT, OUTM, FLOOR>(P, acc[cur], sc[i], orow, qb, yb, HW, relu_floor, true);
       __syncwarp();
@@ -682,12 +751,17 @@ template <int NS, int EPI, int RS, int COUT, int OUTM, bool FLOOR, int EPI_WARPS
 __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ewarp, const int lane, const uint32_t tmem_base,
                                                uint64_t* acc_full, uint64_t* acc_empty,
                                                const uint4* __restrict__ shortcut, uint4* __restrict__ out,
-                                               int8_t* __restrict__ q5, float* __restrict__ y, const FqArgs& fa) {
+                                               int8_t* __restrict__ q5, float* __restrict__ y, const FqArgs& fa,
+                                               const uint8_t* sc_buf = nullptr, uint64_t* sc_full = nullptr,
+                                               uint64_t* sc_empty = nullptr) {
   constexpr int NCOLS = 16 * NS;
   constexpr int NSLOT = TMEM_COLS / NCOLS;
   constexpr int NWG = EPI_WARPS / 4;
   constexpr int RG = GroupRows<NS>::value;
   constexpr int NGS = NSLOT / RG;               // group slots
+  int sst = 0;                                  // EPI_RESIDUAL: shortcut stage ring position / phase parity
+  uint32_t sph = 0;
+  const bool sc_tma = (EPI == EPI_RESIDUAL) && P.sc_stages > 0;
   const int wg = ewarp >> 2;                    // warpgroup
   const int quarter = ewarp & 3;                // TMEM lane quarter this warp may access (== warp id % 4)
   const int ox = quarter * 32 + lane;           // pitch == UMMA_M: a slot is one output row of the tile, lane is the column
@@ -740,7 +814,19 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
     // exe_mode 0: this tile's frame constants, and the running (min, max) of what this warp produces for the frame
     FqFrameParams fq;
     float vmin = INFINITY, vmax = -INFINITY;
-    if (EPI == EPI_FQ) fq = fa.fp[b];
+    float2 fq_bias2[8];                     // this frame's fake-quantised bias in accumulator-column pairs
+    int fq_slow = 0;                        // 0: fast, 1: fast with clamps, 2: general form (operand offset)
+    if (EPI == EPI_FQ) {
+      fq = fa.fp[b];
+      fq_slow = (fq.dmin != 0) ? 2 : ((fq.clamp_acc || fq.clamp_add) ? 1 : 0);         // per frame: warp-uniform
+#pragma unroll
+      for (int k = 0; k < 8; ++k) fq_bias2[k] = make_float2(fq.bias[chan_of_byte(2 * k)], fq.bias[chan_of_byte(2 * k + 1)]);
+    }
+    const uint4* sc_tile = nullptr;
+    if (sc_tma) {                                 // this tile's shortcut rows have landed in shared memory
+      mbar_wait(&sc_full[sst], sph);
+      sc_tile = reinterpret_cast<const uint4*>(sc_buf + (size_t)sst * P.sc_stage_bytes) + ox;
+    }
     const int first = (int)((wg + NWG - (G0 % NWG)) % NWG);
     for (int j = first; j < ngrp; j += NWG) {
       const uint32_t G = G0 + j;
@@ -755,7 +841,8 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
       mbar_wait(&acc_full[G % NSLOT], (G / NSLOT) & 1);
       tc_fence_after();
       epilogue_group<NS, EPI, RS, COUT, OUTM, FLOOR>(P, cnt, taddr0, cinit, shortcut + prow, out + prow, qb, yb, HW, relu_floor, valid,
-                                                     &acc_empty[slot0 / RG], lane, wg, fa, fq, prow, y0 + mb0, gx, vmin, vmax);
+                                                     &acc_empty[slot0 / RG], lane, wg, fa, fq, prow, y0 + mb0, gx, vmin, vmax,
+                                                     sc_tile ? sc_tile + mb0 * UMMA_M : nullptr, fq_bias2, fq_slow);
       if (!X_ROWARRIVE) {
         tmem_st_wait();                    // warp-collective: every lane's re-arm stores have landed
         tc_fence_before();
@@ -763,6 +850,11 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
       }
     }
     G0 += ngrp;
+    if (sc_tma) {                           // every epilogue warp releases the shortcut buffer, with or without groups in the tile
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sc_empty[sst]);
+      if (++sst == P.sc_stages) { sst = 0; sph ^= 1; }
+    }
     if (EPI == EPI_FQ) {                    // one atomic pair per warp and tile (a tile never spans frames)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -909,19 +1001,23 @@ template <int KS, int NS, int EPI, int RS, int COUT, int OUTM, bool FLOOR, int E
 __global__ void __launch_bounds__((CTRL_WARPS + EPI_WARPS) * 32, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ UmmaParams P,
                  const uint8_t* __restrict__ w_img, const uint4* __restrict__ shortcut, uint4* __restrict__ out,
-                 int8_t* __restrict__ q5, float* __restrict__ y, const __grid_constant__ FqArgs fa) {
+                 int8_t* __restrict__ q5, float* __restrict__ y, const __grid_constant__ FqArgs fa,
+                 const __grid_constant__ CUtensorMap smap) {
   constexpr int NCOLS = 16 * NS;
   constexpr int NSLOT = TMEM_COLS / NCOLS;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* const tile0 = smem;
-  uint8_t* const w_s = smem + (size_t)P.stages * P.stage_bytes;
+  uint8_t* const sc0 = smem + (size_t)P.stages * P.stage_bytes;              // EPI_RESIDUAL: shortcut tile buffers
+  uint8_t* const w_s = sc0 + (size_t)P.sc_stages * P.sc_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + ((P.w_bytes + 127) & ~127u));
   uint64_t* tile_full = bars;                            // [MAX_STAGES]
   uint64_t* tile_empty = bars + MAX_STAGES;              // [MAX_STAGES]
   uint64_t* acc_full = bars + 2 * MAX_STAGES;            // [NSLOT]
   uint64_t* acc_empty = bars + 2 * MAX_STAGES + NSLOT;   // [NSLOT]
-  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * NSLOT);
+  uint64_t* sc_full = bars + 2 * MAX_STAGES + 2 * NSLOT; // [MAX_STAGES]
+  uint64_t* sc_empty = sc_full + MAX_STAGES;             // [MAX_STAGES]
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(sc_empty + MAX_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -935,11 +1031,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(&tile_full[i], 1);
       mbar_init(&tile_empty[i], P.nbw);
+      mbar_init(&sc_full[i], 1);
+      mbar_init(&sc_empty[i], EPI_WARPS);
     }
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], X_ROWARRIVE ? 4 * GroupRows<NS>::value : 4);   // one elected arrival per epilogue warp of the consuming warpgroup
     }
+    if (EPI == EPI_RESIDUAL && P.sc_stages > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&smap)) : "memory");
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_base_s, TMEM_COLS);
@@ -953,8 +1052,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      int st = 0;
-      uint32_t ph = 0;                       // phase parity of the current pass over the stage ring
+      int st = 0, sst = 0;
+      uint32_t ph = 0, sph = 0;              // phase parity of the current pass over the stage rings
       for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
         mbar_wait(&tile_empty[st], ph ^ 1);
         const int b = t / tiles_per_frame;
@@ -963,6 +1062,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         mbar_arrive_expect_tx(&tile_full[st], P.box_bytes);
         tma_load_3d(tile0 + (size_t)st * P.stage_bytes, &tmap, (tx * P.TW - P.pad) * 2, ty * P.TH - P.pad, b, &tile_full[st]);
         if (++st == P.stages) { st = 0; ph ^= 1; }
+        if (EPI == EPI_RESIDUAL && P.sc_stages > 0) {
+          // the shortcut pixels of the tile's OUTPUT rows (no halo): consumed by the epilogue, so the 0.5 GB re-read
+          // overlaps the MMAs instead of sitting in front of the residual arithmetic
+          mbar_wait(&sc_empty[sst], sph ^ 1);
+          mbar_arrive_expect_tx(&sc_full[sst], P.sc_stage_bytes);
+          tma_load_3d(sc0 + (size_t)sst * P.sc_stage_bytes, &smap, tx * P.TW * 2, ty * P.TH, b, &sc_full[sst]);
+          if (++sst == P.sc_stages) { sst = 0; sph ^= 1; }
+        }
       }
     }
   } else if (warp < CTRL_WARPS) {
@@ -997,7 +1104,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     // ================= epilogue =================
     constexpr bool PIN = !X_NOPIN && NS == 1 && (EPI == EPI_PLAIN || (EPI == EPI_FINAL && OUTM != 0));
     epilogue_warps<NS, EPI, RS, COUT, OUTM, FLOOR, EPI_WARPS, PIN>(P, warp - CTRL_WARPS, lane, tmem_base, acc_full, acc_empty,
-                                                                   shortcut, out, q5, y, fa);
+                                                                   shortcut, out, q5, y, fa, sc0, sc_full, sc_empty);
   }
 
   // ---- teardown ----
@@ -1323,13 +1430,14 @@ static EncodeTiledFn get_encode_fn() {
 // Tuning knobs from the environment, read once per process (first use).  They select among correct variants only; the
 // knock-out masks that produce wrong results exist only in -DSESRQ_DEBUG_KNOBS builds.
 struct Tuning {
-  int nbw = 0, nbw_l0 = 0, nbw_final = 0, l0_no_tma = 0, l0_xstages = 0, dbg = 0;
+  int nbw = 0, nbw_l0 = 0, nbw_final = 0, l0_no_tma = 0, l0_xstages = 0, sc_no_tma = 0, dbg = 0;
   Tuning() {
     auto geti = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; };
     nbw = geti("SESRQ_UMMA_NBW");
     nbw_l0 = geti("SESRQ_UMMA_NBW_L0");
     nbw_final = geti("SESRQ_UMMA_NBW_FINAL");
     l0_no_tma = getenv("SESRQ_L0_NO_TMA") ? 1 : 0;
+    sc_no_tma = getenv("SESRQ_SC_NO_TMA") ? 1 : 0;
     l0_xstages = geti("SESRQ_L0_XSTAGES");
 #ifdef SESRQ_DEBUG_KNOBS
     dbg = geti("SESRQ_UMMA_DBG");
@@ -1523,12 +1631,12 @@ int umma_prepare_layer(LayerDev& L, const int8_t* w) {
 template <int KS, int NS, int EPI, int RS, int COUT, int OUTM, bool FLOOR, int EPI_WARPS>
 static int launch_one(const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L, const uint8_t* d_shortcut,
                       uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem, cudaStream_t st,
-                      const FqArgs& fa = FqArgs{}) {
+                      const FqArgs& fa = FqArgs{}, const CUtensorMap* smap = nullptr) {
   auto kern = conv_umma_kernel<KS, NS, EPI, RS, COUT, OUTM, FLOOR, EPI_WARPS>;
   static std::atomic<uint64_t> optin_done{0};
   if (int rc = ensure_smem_optin(kern, 227 * 1024, optin_done)) return rc;
   kern<<<grid, (CTRL_WARPS + EPI_WARPS) * 32, smem, st>>>(tmap, P, L.d_wumma, reinterpret_cast<const uint4*>(d_shortcut),
-                                                          reinterpret_cast<uint4*>(d_out), d_q5, d_y, fa);
+                                                          reinterpret_cast<uint4*>(d_out), d_q5, d_y, fa, smap ? *smap : tmap);
   SESRQ_LAUNCH_CHECK("conv_umma_kernel");
   return SESRQ_OK;
 }
@@ -1536,9 +1644,10 @@ static int launch_one(const CUtensorMap& tmap, const UmmaParams& P, const LayerD
 template <int KS, int NS, int EPI_WARPS>
 static int launch_epi(const LayerConst& c, const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L,
                       const uint8_t* d_shortcut, uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem,
-                      cudaStream_t st) {
+                      cudaStream_t st, const CUtensorMap* smap) {
 #define SESRQ_GO(EPI_, RS_, COUT_, OUTM_, FLOOR_) \
-  return launch_one<KS, NS, EPI_, RS_, COUT_, OUTM_, FLOOR_, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st)
+  return launch_one<KS, NS, EPI_, RS_, COUT_, OUTM_, FLOOR_, EPI_WARPS>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, \
+                                                                        FqArgs{}, smap)
 #define SESRQ_GO_FINAL(RS_, COUT_)                              \
   do {                                                          \
     if (d_q5 && d_y) SESRQ_GO(EPI_FINAL, RS_, COUT_, 0, false); \
@@ -1563,10 +1672,10 @@ static int launch_epi(const LayerConst& c, const CUtensorMap& tmap, const UmmaPa
 template <int KS>
 static int launch_ns(int ns, const LayerConst& c, const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L,
                      const uint8_t* d_shortcut, uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem,
-                     cudaStream_t st) {
-  if (ns == 1) return launch_epi<KS, 1, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
-  if (ns == 2) return launch_epi<KS, 2, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
-  return launch_epi<KS, 4, 8>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+                     cudaStream_t st, const CUtensorMap* smap) {
+  if (ns == 1) return launch_epi<KS, 1, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, smap);
+  if (ns == 2) return launch_epi<KS, 2, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, smap);
+  return launch_epi<KS, 4, 8>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, smap);
 }
 
 // Tile height = TB * nbw rows (nbw issuer warps / row bands).  More bands = more MMA issue bandwidth but (k - 1)
@@ -1741,7 +1850,7 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
 
 // Tiling, tensor map and kernel parameters of one 16-channel-layout launch (shared by the integer and fake-quant paths).
 static int plan_conv_launch(const LayerDev& L, const uint8_t* d_in, int B, int H, int W, UmmaParams& P, CUtensorMap& tmap,
-                            int& grid, size_t& smem) {
+                            int& grid, size_t& smem, const uint8_t* d_shortcut = nullptr, CUtensorMap* smap = nullptr) {
   const LayerConst& c = L.c;
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return SESRQ_EUNSUPPORTED;
@@ -1756,8 +1865,15 @@ static int plan_conv_launch(const LayerDev& L, const uint8_t* d_in, int B, int H
   P.TW = cdiv(W, P.tiles_x);
   const int pairs = (c.k + 1) / 2;
   const uint32_t w_bytes = (uint32_t)pairs * 2 * c.k * N * 16;
-  const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (2 * MAX_STAGES + 2 * (TMEM_COLS / N)) + 64 + 1024;
+  size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (4 * MAX_STAGES + 2 * (TMEM_COLS / N)) + 64 + 1024;
   const int sms = sm_count();
+  // residual layer: the shortcut rows of a tile are staged by TMA as well (16 rows x 2 KB per buffer, 3 buffers: a
+  // buffer lives until the epilogue is through with the tile, i.e. longer than the input tile the MMAs consume)
+  const bool sc_tma = c.epi == EPI_RESIDUAL && d_shortcut && smap && ns == 1 && !tuning().sc_no_tma &&
+                      (reinterpret_cast<uintptr_t>(d_shortcut) & 15) == 0;
+  const int sc_stages = sc_tma ? 3 : 0;
+  const size_t sc_reserved = (size_t)sc_stages * (2 * TB) * UMMA_M * 16;
+  fixed += sc_reserved;
   // slack: the last row's rightmost K chunk reaches 2*pad + 1 pixels past the row
   // measured: 16-channel layers are fastest with 2 bands (TH = 16: the 32-slot ring then holds two tiles; 1080p x2 3x3
   // 0.178 vs 0.185 ms with 3 bands); the 16-output x4 final layer with 3 (540x960: 0.909 vs 0.955 ms)
@@ -1774,11 +1890,27 @@ static int plan_conv_launch(const LayerDev& L, const uint8_t* d_in, int B, int H
   P.w_bytes = w_bytes;
   P.num_tiles = P.tiles_x * P.tiles_y * B;
   P.B = B; P.H = H; P.W = W; P.pad = pad;
+  P.sc_stages = sc_stages;
+  P.sc_stage_bytes = (uint32_t)(P.TH * UMMA_M * 16);
   // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32, A = u8, B = s8, K-major both, M = 128;
   // N is OR-ed in per instruction (mma_issue_tile)
   P.idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(UMMA_M >> 4) << 24);
   fill_epilogue_params(P, c, ns);
   P.dbg = tuning().dbg;
+
+  if (sc_tma) {                         // the shortcut tensor has the input's layout; box = the tile's output rows, no halo
+    cuuint64_t sdim[3] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t sstr[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+    cuuint32_t sbox[3] = {(cuuint32_t)UMMA_M * 2, (cuuint32_t)P.TH, 1};
+    cuuint32_t sest[3] = {1, 1, 1};
+    CUresult sr = encode(smap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t*>(d_shortcut), sdim, sstr, sbox, sest,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (sr != CUDA_SUCCESS) {
+      set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (shortcut)");
+      return SESRQ_ECUDA;
+    }
+  }
 
   // ---- tensor map over the NHWC16 input viewed as (W*2 x 8-byte, H, B) ----
   cuuint64_t gdim[3] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)B};
@@ -1793,7 +1925,8 @@ static int plan_conv_launch(const LayerDev& L, const uint8_t* d_in, int B, int H
     return SESRQ_ECUDA;
   }
   grid = std::min(P.num_tiles, sms);
-  smem = (size_t)P.stage_bytes * P.stages + fixed;
+  // `fixed` reserved 3 shortcut buffers of 2 * TB rows; the tile may have come out shorter
+  smem = (size_t)P.stage_bytes * P.stages + fixed - sc_reserved + (size_t)P.sc_stages * P.sc_stage_bytes;
   return SESRQ_OK;
 }
 
@@ -1802,13 +1935,14 @@ int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, c
   const LayerConst& c = L.c;
   if (is_l0_layout(c)) return launch_conv_umma_l0(L, d_x, d_out, B, H, W, st);
   UmmaParams P;
-  CUtensorMap tmap;
+  CUtensorMap tmap, smap;
   int grid = 0;
   size_t smem = 0;
-  if (int rc = plan_conv_launch(L, d_in, B, H, W, P, tmap, grid, smem)) return rc;
+  if (int rc = plan_conv_launch(L, d_in, B, H, W, P, tmap, grid, smem, d_shortcut, &smap)) return rc;
   const int ns = L.umma_n / 16;
-  if (c.k == 3) return launch_ns<3>(ns, c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
-  return launch_ns<5>(ns, c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st);
+  const CUtensorMap* sp = P.sc_stages > 0 ? &smap : nullptr;
+  if (c.k == 3) return launch_ns<3>(ns, c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, sp);
+  return launch_ns<5>(ns, c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, sp);
 }
 
 // exe_mode 0: four PE-masked accumulator sets (the float-domain PE sums are rounded separately, quan_func.py:333,:386),
