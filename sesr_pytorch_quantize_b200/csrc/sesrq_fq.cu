@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(256) fqb_quant_nchw_kernel(const float* __rest
   const int f = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
-  const float sf = fp[f].in_s, zf = fp[f].in_z;
+  const float zf = fp[f].in_z;
+  const ExactDiv div_s(fp[f].in_s);                       // x / s, exactly rounded (sesrq_common.cuh)
   const float* xb = x + (size_t)f * C * HW + p;
   uint4* act = act_all + (size_t)f * HW;
   const int i = p;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(256) fqb_quant_nchw_kernel(const float* __rest
 #pragma unroll
   for (int c = 0; c < SESRQ_MAX_CH; ++c) {
     if (c < C) {
-      const int q = quant_add_zero(__fdiv_rn(__ldg(xb + (long long)c * HW), sf), zf);
+      const int q = quant_add_zero(div_s(__ldg(xb + (long long)c * HW)), zf);
       const int j = (c & 3) * 4 + (c >> 2);
       w[j >> 2] |= (uint32_t)(q + 128) << (8 * (j & 3));
     }
@@ -147,12 +148,13 @@ __global__ void __launch_bounds__(256) fqb_quant_nhwc_kernel(const float4* __res
   const unsigned t = tf;
   uint32_t w = 0u;
   if (live) {
-    const float sf = fp[f].in_s, zf = fp[f].in_z;
+    const float zf = fp[f].in_z;
+    const ExactDiv div_s(fp[f].in_s);
     const float4 v = __ldg(x + t);
-    const uint32_t b0 = (uint32_t)(quant_add_zero(__fdiv_rn(v.x, sf), zf) + 128);
-    const uint32_t b1 = (uint32_t)(quant_add_zero(__fdiv_rn(v.y, sf), zf) + 128);
-    const uint32_t b2 = (uint32_t)(quant_add_zero(__fdiv_rn(v.z, sf), zf) + 128);
-    const uint32_t b3 = (uint32_t)(quant_add_zero(__fdiv_rn(v.w, sf), zf) + 128);
+    const uint32_t b0 = (uint32_t)(quant_add_zero(div_s(v.x), zf) + 128);
+    const uint32_t b1 = (uint32_t)(quant_add_zero(div_s(v.y), zf) + 128);
+    const uint32_t b2 = (uint32_t)(quant_add_zero(div_s(v.z), zf) + 128);
+    const uint32_t b3 = (uint32_t)(quant_add_zero(div_s(v.w), zf) + 128);
     w = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);                              // byte e = this lane's contribution to word e
   }
   // transpose: lane q ends with (lane0.byte q, lane1.byte q, lane2.byte q, lane3.byte q)
@@ -219,9 +221,10 @@ __global__ void __launch_bounds__(256) fqb_final_kernel(const float4* __restrict
   float v[4] = {v4.x, v4.y, v4.z, v4.w};
   if (do_quant) {
     const float sf = fp[f].in_s, zf = fp[f].in_z;
+    const ExactDiv div_s(sf);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float qv = (float)quant_add_zero(__fdiv_rn(v[e], sf), zf);
+      const float qv = (float)quant_add_zero(div_s(v[e]), zf);
       v[e] = __fmul_rn(__fsub_rn(qv, zf), sf);                    // :215
     }
   }

@@ -140,6 +140,16 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const int (&r)[16]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+// 16 columns, every word the same value (one source register)
+__device__ __forceinline__ void tmem_st16_const(uint32_t taddr, int v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): two IEEE round-to-nearest operations per issue slot, each lane
@@ -194,6 +204,9 @@ __device__ __forceinline__ uint32_t pack4_sat_s8(int a, int b, int c, int d) {
 // ------------------------------------------------------------------------------------------------
 constexpr int UMMA_M = 128;
 constexpr int TMEM_COLS = 512;
+#ifndef SESRQ_FQ_EPI_WARPS
+#define SESRQ_FQ_EPI_WARPS 8            // epilogue warps of the exe_mode 0 kernels
+#endif
 constexpr int CTRL_WARPS = 4;            // warp 0: TMA producer; warps 1-3: MMA issuers (keeps epilogue warp % 4 == lane quarter)
 constexpr int MAX_STAGES = 4;
 
@@ -596,65 +609,87 @@ __device__ __noinline__ void epilogue_pixel_fq_slow(const FqArgs& fa, const FqFr
 // bit-identical to the general form.  CLAMP: the float-domain PE / adder clamps can fire for this frame's operand range
 // (decided per frame by fqb_params_kernel from the layer's weight mass), otherwise they are skipped as provably inert.
 template <bool CLAMP>
-__device__ __forceinline__ void epilogue_pixel_fq_fast(const FqArgs& fa, const FqFrameParams& f, const float2 (&bias2)[8],
-                                                       const int (&acc)[4][16], float (&o)[16]) {
+__device__ __forceinline__ void epilogue_half_fq_fast(const FqArgs& fa, const float cscale, const float4 cl, const float2 (&bias2)[8],
+                                                      const int h, const int (&a4)[4][8], float (&o)[16]) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int kk = 0; kk < 4; ++kk) {
     // NOTE: the PE sums are scalar adds on purpose.  ptxas contracts `mul.rn.f32x2` feeding `add.rn.f32x2` into one
     // FFMA2 (seen in the SASS: a single rounding, not the reference's two); the scalar add.rn.f32 is never fused.
     float2 s = make_float2(0.f, 0.f);
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      const float2 a = f2_add(make_float2(__int_as_float(acc[p][2 * k]), __int_as_float(acc[p][2 * k + 1])), -MAGIC_F);
-      float2 yp = f2_mul(a, f.cscale);
+      const float2 a = f2_add(make_float2(__int_as_float(a4[p][2 * kk]), __int_as_float(a4[p][2 * kk + 1])), -MAGIC_F);
+      float2 yp = f2_mul(a, cscale);
       if (CLAMP) {
-        yp.x = fminf(fmaxf(yp.x, f.lo_acc), f.hi_acc);                                       // :333
-        yp.y = fminf(fmaxf(yp.y, f.lo_acc), f.hi_acc);
+        yp.x = fminf(fmaxf(yp.x, cl.x), cl.y);                                               // :333
+        yp.y = fminf(fmaxf(yp.y, cl.x), cl.y);
       }
       s.x = __fadd_rn(s.x, yp.x);                                                            // :386 (first add: 0 + y_0)
       s.y = __fadd_rn(s.y, yp.y);
     }
     if (CLAMP) {
-      s.x = fminf(fmaxf(s.x, f.lo_add), f.hi_add);                                           // :434
-      s.y = fminf(fmaxf(s.y, f.lo_add), f.hi_add);
+      s.x = fminf(fmaxf(s.x, cl.z), cl.w);                                                   // :434
+      s.y = fminf(fmaxf(s.y, cl.z), cl.w);
     }
-    s = f2_add2(s, bias2[k]);                                                                // :459
+    // bias pair k = 4h + kk
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+      if (hh == h) s = f2_add2(s, bias2[4 * hh + kk]);                                       // :459
     if (fa.relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); }
-    o[chan_of_byte(2 * k)] = s.x;
-    o[chan_of_byte(2 * k + 1)] = s.y;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+      if (hh == h) { o[chan_of_byte(8 * hh + 2 * kk)] = s.x; o[chan_of_byte(8 * hh + 2 * kk + 1)] = s.y; }
   }
 }
 
-__device__ __forceinline__ void epilogue_pixel_fq(const FqArgs& fa, const FqFrameParams& f, const float2 (&bias2)[8],
-                                                  const int mode, const int (&acc)[4][16], float* __restrict__ xo,
-                                                  const float* __restrict__ xr, const bool valid, const int gy, const int gx,
-                                                  const int H, const int W, const int ks, float& vmin, float& vmax) {
-  float4 res[4];
-  if (xr != nullptr && valid) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) res[q] = __ldg(reinterpret_cast<const float4*>(xr) + q);
-  }
+// One output row of the exe_mode 0 path (the accumulator group is one row, GroupRows<4>): the 64 accumulator columns are
+// read in two halves of 8 columns x 4 PEs (32 registers live instead of 64, so that 16 epilogue warps fit the register
+// file), the slot is re-armed with the MAGIC constant, and the 16 channels go out as four float4.
+__device__ __forceinline__ void epilogue_row_fq(const FqArgs& fa, const FqFrameParams* __restrict__ fpb, const float cscale,
+                                                const float4 cl, const float2 (&bias2)[8], const int mode, const uint32_t taddr,
+                                                float* __restrict__ xo, const float* __restrict__ xr, const bool valid,
+                                                const int gy, const int gx, const int H, const int W, const int ks, float& vmin,
+                                                float& vmax) {
   float o[16];
-  if (mode == 2) {                          // operand offset: out of line, on a copy
+  if (mode == 2) {                          // operand offset: general form, out of line, on a copy in local memory
     int acc_l[64];
     float o_l[16];
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+    for (int p = 0; p < 4; ++p) {
+      int t16[16];
+      tmem_ld16(taddr + p * 16, t16);
+      tmem_ld_wait();
+      reg_fence16(t16);
 #pragma unroll
-      for (int n = 0; n < 16; ++n) acc_l[p * 16 + n] = acc[p][n];
+      for (int n = 0; n < 16; ++n) acc_l[p * 16 + n] = t16[n];
+    }
+    const FqFrameParams f = *fpb;
     epilogue_pixel_fq_slow(fa, f, acc_l, o_l, gy, gx, H, W, ks);
 #pragma unroll
     for (int c = 0; c < 16; ++c) o[c] = o_l[c];
-  } else if (mode == 1) {
-    epilogue_pixel_fq_fast<true>(fa, f, bias2, acc, o);
   } else {
-    epilogue_pixel_fq_fast<false>(fa, f, bias2, acc, o);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int a4[4][8];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) tmem_ld8(taddr + p * 16 + 8 * h, a4[p]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        asm volatile("" : "+r"(a4[p][0]), "+r"(a4[p][1]), "+r"(a4[p][2]), "+r"(a4[p][3]), "+r"(a4[p][4]), "+r"(a4[p][5]),
+                     "+r"(a4[p][6]), "+r"(a4[p][7]));
+      if (mode == 1) epilogue_half_fq_fast<true>(fa, cscale, cl, bias2, h, a4, o);
+      else epilogue_half_fq_fast<false>(fa, cscale, cl, bias2, h, a4, o);
+    }
   }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) tmem_st16_const(taddr + p * 16, MAGIC_BITS);     // re-arm; awaited by the caller
   if (xr != nullptr && valid) {                                                              // AddOp (models/sesr.py:45)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float2 lo = f2_add2(make_float2(o[4 * q], o[4 * q + 1]), make_float2(res[q].x, res[q].y));
-      const float2 hi = f2_add2(make_float2(o[4 * q + 2], o[4 * q + 3]), make_float2(res[q].z, res[q].w));
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(xr) + q);
+      const float2 lo = f2_add2(make_float2(o[4 * q], o[4 * q + 1]), make_float2(r4.x, r4.y));
+      const float2 hi = f2_add2(make_float2(o[4 * q + 2], o[4 * q + 3]), make_float2(r4.z, r4.w));
       o[4 * q] = lo.x; o[4 * q + 1] = lo.y; o[4 * q + 2] = hi.x; o[4 * q + 3] = hi.y;
     }
   }
@@ -687,11 +722,18 @@ __device__ __forceinline__ void epilogue_group(const UmmaParams& P, const int cn
                                                const uint4* __restrict__ sc_row, uint4* __restrict__ orow,
                                                int8_t* __restrict__ qb, float* __restrict__ yb, const long long HW,
                                                const float relu_floor, const bool valid, uint64_t* empty_bar, const int lane,
-                                               const int wg, const FqArgs& fa, const FqFrameParams& fq, const long long fq_px,
+                                               const int wg, const FqArgs& fa, const FqFrameParams* __restrict__ fpb, const float fq_cscale,
+                                               const float4 fq_cl, const long long fq_px,
                                                const int gy0, const int gx, float& vmin, float& vmax,
                                                const uint4* __restrict__ sc_smem, const float2 (&fq_bias2)[8], const int fq_slow) {
   constexpr int NCOLS = 16 * NS;
   constexpr int RG = GroupRows<NS>::value;
+  if constexpr (EPI == EPI_FQ && NS == 4) {                   // exe_mode 0: one row per group, own TMEM access pattern
+    static_assert(RG == 1, "the fake-quant epilogue handles one row per group");
+    epilogue_row_fq(fa, fpb, fq_cscale, fq_cl, fq_bias2, fq_slow, taddr0, fa.xout + fq_px * 16,
+                    fa.xres ? fa.xres + fq_px * 16 : nullptr, valid && cnt > 0, gy0, gx, P.H, P.W, 2 * P.pad + 1, vmin, vmax);
+    return;
+  }
   uint4 sc[RG];
 #pragma unroll
   for (int i = 0; i < RG; ++i) {
@@ -718,11 +760,7 @@ __device__ __forceinline__ void epilogue_group(const UmmaParams& P, const int cn
     slot_store<NS>(taddr0 + (uint32_t)(i * NCOLS), cinit);      // re-arm the slot; awaited once per group
     const bool v_i = valid && i < cnt;
     if (SESRQ_X_ROWSYNC == 2 || (SESRQ_X_ROWSYNC == 1 && EPI == EPI_FINAL)) asm volatile("bar.sync %0, 128;" ::"r"(2 + wg) : "memory");
-    if constexpr (EPI == EPI_FQ && NS == 4) {
-      const long long px = fq_px + (long long)i * P.W;
-      epilogue_pixel_fq(fa, fq, fq_bias2, fq_slow, acc[cur], fa.xout + px * 16, fa.xres ? fa.xres + px * 16 : nullptr, v_i, gy0 + i,
-                        gx, P.H, P.W, 2 * P.pad + 1, vmin, vmax);
-    } else if (BRANCH) {
+    if (BRANCH) {
       if (v_i) epilogue_pixel<NS, EPI, RS, COUT, OUTM, FLOOR>(P, acc[cur], sc[i], orow, qb, yb, HW, relu_floor, true);
       __syncwarp();
     } else {
@@ -812,15 +850,19 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
       if (OUTM != 1) yb_tile = y + (long long)b * (P.cout / R2) * (HW * R2) + (long long)y0 * RS * (P.W * RS) + (long long)gx * RS;
     }
     // exe_mode 0: this tile's frame constants, and the running (min, max) of what this warp produces for the frame
-    FqFrameParams fq;
+    const FqFrameParams* fpb = nullptr;
     float vmin = INFINITY, vmax = -INFINITY;
     float2 fq_bias2[8];                     // this frame's fake-quantised bias in accumulator-column pairs
+    float fq_cscale = 0.f;
+    float4 fq_cl = make_float4(0.f, 0.f, 0.f, 0.f);
     int fq_slow = 0;                        // 0: fast, 1: fast with clamps, 2: general form (operand offset)
     if (EPI == EPI_FQ) {
-      fq = fa.fp[b];
-      fq_slow = (fq.dmin != 0) ? 2 : ((fq.clamp_acc || fq.clamp_add) ? 1 : 0);         // per frame: warp-uniform
+      fpb = fa.fp + b;
+      fq_slow = (fpb->dmin != 0) ? 2 : ((fpb->clamp_acc || fpb->clamp_add) ? 1 : 0);   // per frame: warp-uniform
+      fq_cscale = fpb->cscale;
+      fq_cl = make_float4(fpb->lo_acc, fpb->hi_acc, fpb->lo_add, fpb->hi_add);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) fq_bias2[k] = make_float2(fq.bias[chan_of_byte(2 * k)], fq.bias[chan_of_byte(2 * k + 1)]);
+      for (int k = 0; k < 8; ++k) fq_bias2[k] = make_float2(fpb->bias[chan_of_byte(2 * k)], fpb->bias[chan_of_byte(2 * k + 1)]);
     }
     const uint4* sc_tile = nullptr;
     if (sc_tma) {                                 // this tile's shortcut rows have landed in shared memory
@@ -841,7 +883,7 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
       mbar_wait(&acc_full[G % NSLOT], (G / NSLOT) & 1);
       tc_fence_after();
       epilogue_group<NS, EPI, RS, COUT, OUTM, FLOOR>(P, cnt, taddr0, cinit, shortcut + prow, out + prow, qb, yb, HW, relu_floor, valid,
-                                                     &acc_empty[slot0 / RG], lane, wg, fa, fq, prow, y0 + mb0, gx, vmin, vmax,
+                                                     &acc_empty[slot0 / RG], lane, wg, fa, fpb, fq_cscale, fq_cl, prow, y0 + mb0, gx, vmin, vmax,
                                                      sc_tile ? sc_tile + mb0 * UMMA_M : nullptr, fq_bias2, fq_slow);
       if (!X_ROWARRIVE) {
         tmem_st_wait();                    // warp-collective: every lane's re-arm stores have landed
@@ -1131,36 +1173,14 @@ constexpr int L0_XP = 136;               // fp32 tile row pitch in floats = TMA 
                                          // (the box must start on a 16-byte boundary: an unaligned inner coordinate faults)
 constexpr int L0_XSTAGES = 4;            // fp32 tile buffers (upper bound; P.xstages are used)
 
-// x / s with a hoisted reciprocal.  `rcp` is the Newton-refined reciprocal of s; the three operations are
-// exactly the quotient steps of div.rn.f32's fast path (q0 = x*rcp; e = fma(-s, q0, x); q = fma(rcp, e, q0)),
-// which is correctly rounded whenever neither the operands nor the quotient are near the exponent limits.
-// Tiny |x| (< 2^-100): the code is decided by the zero point, not by the last bit of the quotient.  Huge |x|
-// would overflow the quotient (Inf - Inf = NaN in the residual), so x is first clamped to +-lim with
-// lim / s = 2^40: beyond it the code is saturated whatever the int32 zero point is.  The quantised result is
-// therefore identical to true division for every finite input (tests: rounding-boundary / extreme inputs).
-struct ExactDiv {
-  float s, rcp, lim;
-  __device__ __forceinline__ explicit ExactDiv(float s_) : s(s_) {
-    float y0;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(s_));
-    rcp = __fmaf_rn(y0, __fmaf_rn(-s_, y0, 1.0f), y0);
-    lim = fminf(__fmul_rn(s_, 1099511627776.f), 1.2676506e30f);      // min(s * 2^40, 2^100)
-  }
-  __device__ __forceinline__ float operator()(float x) const {
-    x = fminf(fmaxf(x, -lim), lim);
-    const float q0 = __fmul_rn(x, rcp);
-    const float e = __fmaf_rn(-s, q0, x);
-    return __fmaf_rn(rcp, e, q0);
-  }
-  // two quotients per instruction (FMUL2 / FFMA2): lane-wise identical to the scalar sequence
-  __device__ __forceinline__ float2 operator()(float2 x) const {
-    x.x = fminf(fmaxf(x.x, -lim), lim);
-    x.y = fminf(fmaxf(x.y, -lim), lim);
-    const float2 q0 = f2_mul(x, rcp);
-    const float2 e = f2_fma3(make_float2(-s, -s), q0, x);
-    return f2_fma3(make_float2(rcp, rcp), e, q0);
-  }
-};
+// ExactDiv (sesrq_common.cuh) on two quotients per instruction (FMUL2 / FFMA2): lane-wise identical to the scalar sequence
+__device__ __forceinline__ float2 exact_div2(const ExactDiv& d, float2 x) {
+  x.x = fminf(fmaxf(x.x, -d.lim), d.lim);
+  x.y = fminf(fmaxf(x.y, -d.lim), d.lim);
+  const float2 q0 = f2_mul(x, d.rcp);
+  const float2 e = f2_fma3(make_float2(-d.s, -d.s), q0, x);
+  return f2_fma3(make_float2(d.rcp, d.rcp), e, q0);
+}
 
 template <int KS, int NS, int CIN, bool FLOOR, int EPI_WARPS>
 __global__ void __launch_bounds__((CTRL_WARPS + EPI_WARPS + L0_BUILD_WARPS) * 32, 1)
@@ -1316,7 +1336,7 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
             int q[2][4] = {{-128, -128, -128, -128}, {-128, -128, -128, -128}};   // unused channels: byte 0 (zero weights)
 #pragma unroll
             for (int c = 0; c < CIN; ++c) {
-              const float2 tq = f2_add(div_s0(make_float2(v[u][c], v[u + 1][c])), z0);   // :225, clamped by the pack
+              const float2 tq = f2_add(exact_div2(div_s0, make_float2(v[u][c], v[u + 1][c])), z0);   // :225, clamped by the pack
               q[0][c] = __float2int_rn(tq.x);
               q[1][c] = __float2int_rn(tq.y);
             }
@@ -1957,8 +1977,8 @@ int launch_conv_umma_fq(const LayerDev& L, const uint8_t* d_in, const FqArgs& fa
   if (int rc = plan_conv_launch(L, d_in, B, H, W, P, tmap, grid, smem)) return rc;
   for (int p = 0; p < 4; ++p)
     for (int n = 0; n < 16; ++n) P.c_init[p][n] = MAGIC_BITS;
-  if (c.k == 3) return launch_one<3, 4, EPI_FQ, 1, 0, 0, false, 8>(tmap, P, L, nullptr, nullptr, nullptr, nullptr, grid, smem, st, fa);
-  return launch_one<5, 4, EPI_FQ, 1, 0, 0, false, 8>(tmap, P, L, nullptr, nullptr, nullptr, nullptr, grid, smem, st, fa);
+  if (c.k == 3) return launch_one<3, 4, EPI_FQ, 1, 0, 0, false, SESRQ_FQ_EPI_WARPS>(tmap, P, L, nullptr, nullptr, nullptr, nullptr, grid, smem, st, fa);
+  return launch_one<5, 4, EPI_FQ, 1, 0, 0, false, SESRQ_FQ_EPI_WARPS>(tmap, P, L, nullptr, nullptr, nullptr, nullptr, grid, smem, st, fa);
 }
 
 }  // namespace sesrq
