@@ -60,6 +60,7 @@ struct SesrqNet {
   std::vector<int8_t> h_w[SESRQ_NUM_LAYERS];
   bool need_rc = false;       // z_1 != -128: shortcut codes differ from q_1 (quan_func.py:250 vs :280)
   bool need_a0 = false;       // layer 0 runs on the generic path -> separate input-quantise pass
+  bool fuse12 = false;        // layers 1 + 2 in one launch (sesrq_chain.cu); domain 2 is then never materialised
   int device = 0;
   size_t chunk_bytes = (size_t)2048 << 20;   // activation workspace per pass (SESRQ_CHUNK_MB, read at create)
   int host_chunk = 0;                        // frames per host-pipeline chunk (SESRQ_HOST_CHUNK, read at create; 0 = auto)
@@ -181,6 +182,7 @@ int sesrq_net_create(const SesrqNetDesc* d, SesrqNet** out_net) {
     if (v > 0) net->chunk_bytes = (size_t)v << 20;
   }
   if (const char* e = getenv("SESRQ_HOST_CHUNK")) net->host_chunk = std::max(0, atoi(e));
+  if (const char* e = getenv("SESRQ_FUSE")) net->fuse12 = atoi(e) != 0;
   int zs[SESRQ_NUM_DOMAINS];
   for (int i = 0; i < SESRQ_NUM_LAYERS; ++i) zs[i] = d->layers[i].z_in;
   zs[5] = d->z_out;
@@ -350,6 +352,13 @@ int sesrq_net_forward_i8(const SesrqNet* net, const float* d_x, int B, int H, in
     // layers 1..4
     for (int i = 1; i < SESRQ_NUM_LAYERS; ++i) {
       const LayerDev& L = net->layers[i];
+      if (i == 1 && net->fuse12 && chain2_supported(net->layers[1], net->layers[2])) {
+        ProfScope ps(net, st, 1);                 // both layers in one launch, A[2] is skipped
+        rc = launch_conv_chain2(net->layers[1], net->layers[2], A[1], A[3], nb, H, W, st);
+        if (rc) return rc;
+        i = 2;
+        continue;
+      }
       const uint8_t* sc = (i == 3) ? (net->need_rc ? RC : A[1]) : nullptr;
       uint8_t* out = (i < 4) ? A[i + 1] : nullptr;
       ProfScope ps(net, st, i);

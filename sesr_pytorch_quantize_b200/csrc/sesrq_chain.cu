@@ -1,0 +1,468 @@
+// Two consecutive 3x3 layers of the 16-channel chain in ONE launch (sm_100a only): the codes the first layer produces
+// never go to HBM, they are handed to the second layer through shared memory.
+//
+// The single-layer kernels of sesrq_umma.cu run the plain 3x3 layers at ~92 % of the HBM roofline, so the only way to
+// make the pair faster is to drop the 32 B/px round trip of the intermediate tensor.
+//
+// Work unit: a STRIP = (frame, 124-pixel column block, segment of SH rows), streamed top to bottom through a
+// persistent CTA (one per SM).  Per strip row the data flow is
+//
+//   TMA (warp 0)        16-row blocks of the NHWC16 input, 128 pixels wide (2 halo columns / rows each side, zero-filled
+//                       outside the frame = code -128 = the reference's pad value, quan_func.py:351-352) -> input ring
+//   issuer A (warp 1)   per input row r two tcgen05.mma.kind::i8 (tap pairs) with N = 48: the row contributes to the
+//                       output rows r-2 .. r, whose accumulators are consecutive 16-column TMEM slots (the vertical taps
+//                       are batched into N exactly like sesrq_umma.cu's issue_row); slot ring of 16 rows
+//   epilogue A          8 warps: tcgen05.ld, exact requantisation (epilogue_pixel), codes of out-of-frame
+//   (warps 4-11)        positions forced to byte 0 (they are the NEXT layer's zero padding), 16 B per pixel st.shared into
+//                       the mid ring (32 rows), fence.proxy.async, mbarrier
+//   issuer B (warp 2)   the same MMA pattern on the mid ring rows with the second layer's weights; its own slot ring
+//   epilogue B          8 warps: requantisation, one 16-byte NHWC16 store per pixel to global memory
+//   (warps 12-19)
+//
+// Geometry: input index X of a strip <-> frame column x0 - 2 + X; layer-A output index X <-> x0 - 1 + X (valid for
+// X < 126); layer-B output index X <-> x0 + X (valid for X < 124 = the strip width).  Input row r <-> frame row
+// ys - 2 + r; layer-A output row o <-> ys - 1 + o (SH + 2 rows); layer-B output row o <-> ys + o.
+//
+// Synchronisation: every ring is cut into groups of 8 rows with one (full, empty) mbarrier pair per group position;
+// strips are padded to whole 16-row blocks with PHANTOM groups that travel through the same barriers without work, so
+// that all barriers of a ring stay in the same phase and the parity is a function of the running block counter alone.
+#include <algorithm>
+#include <cstring>
+#include "sesrq_umma_dev.cuh"
+
+namespace sesrq {
+
+constexpr int CH_BLK = 16;                              // rows per ring block = accumulator slots per layer
+constexpr int CH_RG = 8;                                // rows per group (half a block: one epilogue warpgroup each)
+constexpr int CH_GPB = CH_BLK / CH_RG;                  // groups per block
+constexpr int CH_IN_BLOCKS = 3;                         // input ring: 3 x 32 KB
+constexpr int CH_MID_BLOCKS = 2;                        // mid ring:   2 x 32 KB
+constexpr uint32_t CH_ROW_BYTES = UMMA_M * 16;          // one 128-pixel row of NHWC16
+constexpr uint32_t CH_BLK_BYTES = CH_BLK * CH_ROW_BYTES;
+constexpr int CH_EPI_WARPS = 8;                         // per layer: two warpgroups, alternating groups
+constexpr int CH_THREADS = (4 + 2 * CH_EPI_WARPS) * 32;
+constexpr int CH_NCOLS = 16;                            // accumulator columns per row slot (NS = 1)
+constexpr int CH_NTOT = 3 * CH_NCOLS;                   // B image rows per K half (3 vertical taps)
+constexpr uint32_t CH_W_BYTES = 2 * 2 * CH_NTOT * 16;   // 2 tap pairs x 2 K halves
+
+struct ChainGeom {
+  int32_t B, H, W, TW, tiles_x, nseg, SH, num_strips;
+  uint32_t idesc;
+};
+
+struct ChainStrip {
+  int b, x0, ys, sh;                                    // frame, first output column, first output row, output rows
+};
+__device__ __forceinline__ ChainStrip chain_strip(const ChainGeom& G, int s) {
+  ChainStrip t;
+  const int cx = s % G.tiles_x;
+  const int q = s / G.tiles_x;
+  const int seg = q % G.nseg;
+  t.b = q / G.nseg;
+  t.x0 = cx * G.TW;
+  t.ys = seg * G.SH;
+  t.sh = min(G.SH, G.H - t.ys);
+  return t;
+}
+
+// MMAs of one input row: output rows o_lo .. o_hi (at most 3, consecutive) live in slots o % 16; a run that wraps around
+// the slot ring is issued in two pieces.  B row block jblk <-> vertical tap dy = 2 - jblk (sesrq_umma.cu: umma_prepare_layer).
+__device__ __forceinline__ void chain_issue_row(const int r, const int n_out, const uint32_t d_base, const uint32_t a_row_lo,
+                                                const uint32_t w_units, const uint32_t idesc0) {
+  const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t b_lbo = (uint32_t)CH_NTOT << 16;
+  const int o_first = r - 2;
+  const int o_lo = max(o_first, 0);
+  const int o_hi = min(r, n_out - 1);
+  int o = o_lo;
+  while (o <= o_hi) {
+    const int slot = o & (CH_BLK - 1);
+    const int cnt = min(o_hi - o + 1, CH_BLK - slot);
+    const int jblk = o - o_first;
+    const uint32_t idesc = idesc0 | ((uint32_t)((cnt * CH_NCOLS) >> 3) << 17);
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      umma_i8(d_base + (uint32_t)(slot * CH_NCOLS), make_desc(a_row_lo + (uint32_t)(q * 2), desc_hi),
+              make_desc((w_units + (uint32_t)(q * 2 * CH_NTOT + jblk * CH_NCOLS)) | b_lbo, desc_hi), idesc, 1u);
+    o += cnt;
+  }
+}
+
+// One MMA pair (the two tap pairs of a 3x3 row) into consecutive row slots starting at `slot`; B row block jblk; idesc carries N.
+__device__ __forceinline__ void chain_mma_pair(const uint32_t d_base, const uint32_t a_row_lo, const uint32_t w_units,
+                                               const uint32_t idesc, const int slot, const int jblk) {
+  const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t b_lbo = (uint32_t)CH_NTOT << 16;
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+    umma_i8(d_base + (uint32_t)(slot * CH_NCOLS), make_desc(a_row_lo + (uint32_t)(q * 2), desc_hi),
+            make_desc((w_units + (uint32_t)(q * 2 * CH_NTOT + jblk * CH_NCOLS)) | b_lbo, desc_hi), idesc, 1u);
+}
+
+// The warp waits (lane 0: source barrier, lane 1: accumulator barrier, both polled in the same instruction) until the
+// source rows of a half block are present and the row slots it touches first are drained and re-armed.
+__device__ __forceinline__ void chain_wait2(const int lane, const bool need_src, const uint32_t bar_src, const uint32_t par_src,
+                                            const bool need_acc, const uint32_t bar_acc, const uint32_t par_acc) {
+  const bool mine = (lane == 0 && need_src) || (lane == 1 && need_acc);
+  const uint32_t bar = lane == 0 ? bar_src : bar_acc;
+  const uint32_t par = lane == 0 ? par_src : par_acc;
+  uint32_t ok;
+  do {
+    ok = 1u;
+    if (mine)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(ok) : "r"(bar), "r"(par), "r"(MBAR_SUSPEND_NS) : "memory");
+  } while (!__all_sync(0xffffffffu, ok != 0u));
+  tc_fence_after();
+}
+
+// MMA issuer of one layer (one warp, one elected lane issues).  IS_A: source = input ring (one barrier pair per 16-row
+// block, filled by TMA), accumulator slots 0..15; else source = mid ring (one pair per 8-row group, filled by epilogue A),
+// slots 16..31.  INTERIOR blocks (all 16 source rows exist and each has its three output rows: every block of a strip but
+// the first and the last one or two) run a completely unrolled body: slot numbers, B offsets, N and the commit points are
+// compile-time constants and no run-time test is left.  The few edge blocks take a rolled loop (the code must stay small:
+// the instruction cache, not the tensor pipe, limited the first version of this kernel -- profiles/r2_chain.txt).
+template <bool IS_A>
+__device__ __forceinline__ void chain_issuer(const ChainGeom& G, const int lane, const uint32_t tmem_base, const uint8_t* w_s,
+                                             const uint8_t* src_ring, uint64_t* const src_full, uint64_t* const src_empty,
+                                             uint64_t* const acc_full, uint64_t* const acc_empty) {
+  constexpr uint32_t SRC_BLOCKS = IS_A ? CH_IN_BLOCKS : CH_MID_BLOCKS;
+  const uint32_t w_units = (smem_u32(w_s) & 0x3FFFFu) >> 4;
+  const uint32_t src_units = (smem_u32(src_ring) & 0x3FFFFu) >> 4;
+  const uint32_t d_base = tmem_base + (IS_A ? 0u : (uint32_t)(CH_BLK * CH_NCOLS));
+  const uint32_t idesc0 = G.idesc;
+  const uint32_t idesc1 = idesc0 | ((uint32_t)((1 * CH_NCOLS) >> 3) << 17);
+  const uint32_t idesc2 = idesc0 | ((uint32_t)((2 * CH_NCOLS) >> 3) << 17);
+  const uint32_t idesc3 = idesc0 | ((uint32_t)((3 * CH_NCOLS) >> 3) << 17);
+  const uint32_t acc_full_addr = smem_u32(acc_full), acc_empty_addr = smem_u32(acc_empty);
+  const uint32_t src_full_addr = smem_u32(src_full), src_empty_addr = smem_u32(src_empty);
+  uint32_t sb = 0;                                       // running source block counter (input blocks / mid blocks)
+  uint32_t ob = 0;                                       // running output block counter of this layer
+  for (int s = blockIdx.x; s < G.num_strips; s += gridDim.x) {
+    const ChainStrip t = chain_strip(G, s);
+    const int n_src = IS_A ? t.sh + 4 : t.sh + 2;        // source rows that exist
+    const int n_out = n_src - 2;                         // output rows of this layer
+    const int nb_src = (n_src + CH_BLK - 1) / CH_BLK;
+    const int nb_out = (n_out + CH_BLK - 1) / CH_BLK;
+    for (int k = 0; k < nb_src; ++k) {
+      const int r0 = k * CH_BLK;
+      const uint32_t blk = sb + (uint32_t)k;
+      const uint32_t sslot = blk % SRC_BLOCKS;
+      const uint32_t spar = (blk / SRC_BLOCKS) & 1u;
+      const uint32_t opar = (ob + (uint32_t)k) & 1u;
+      const uint32_t a_blk = (src_units + sslot * (CH_BLK * UMMA_M)) | (1u << 16);
+      // barrier addresses of the two halves
+      const uint32_t sfull0 = src_full_addr + (IS_A ? sslot : sslot * CH_GPB) * 8u;
+      const uint32_t sempty0 = src_empty_addr + (IS_A ? sslot : sslot * CH_GPB) * 8u;
+      if (k >= 1 && r0 + CH_BLK - 1 <= n_out - 1) {
+        // ---------------- interior block ----------------
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          chain_wait2(lane, IS_A ? (h == 0) : true, sfull0 + (IS_A ? 0u : (uint32_t)h * 8u), spar, true,
+                      acc_empty_addr + (uint32_t)h * 8u, opar);
+          if (elect_one()) {
+#pragma unroll
+            for (int ii = 0; ii < CH_RG; ++ii) {
+              const int i = h * CH_RG + ii;              // row within the block: output rows r-2 .. r = slots (i-2 .. i) mod 16
+              const uint32_t a_row = a_blk + (uint32_t)(i * UMMA_M);
+              if (i >= 2) {
+                chain_mma_pair(d_base, a_row, w_units, idesc3, i - 2, 0);
+              } else if (i == 1) {
+                chain_mma_pair(d_base, a_row, w_units, idesc1, 15, 0);
+                chain_mma_pair(d_base, a_row, w_units, idesc2, 0, 1);
+              } else {
+                chain_mma_pair(d_base, a_row, w_units, idesc2, 14, 0);
+                chain_mma_pair(d_base, a_row, w_units, idesc1, 0, 2);
+              }
+              if (ii == 1) umma_commit_addr(acc_full_addr + (uint32_t)(1 - h) * 8u);     // output row r-2 closes the other half's group
+              if (IS_A) { if (i == 15) umma_commit_addr(sempty0); }
+              else { if (ii == 7) umma_commit_addr(sempty0 + (uint32_t)h * 8u); }
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // ---------------- edge block (first / last of a strip): rolled, everything decided at run time ----------------
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int rh = r0 + h * CH_RG;
+          if (rh >= n_src) break;
+          chain_wait2(lane, IS_A ? (h == 0) : true, sfull0 + (IS_A ? 0u : (uint32_t)h * 8u), spar, rh < n_out,
+                      acc_empty_addr + (uint32_t)h * 8u, opar);
+          if (elect_one()) {
+#pragma unroll 1
+            for (int ii = 0; ii < CH_RG; ++ii) {
+              const int i = h * CH_RG + ii;
+              const int r = r0 + i;
+              if (r >= n_src) break;
+              chain_issue_row(r, n_out, d_base, a_blk + (uint32_t)(i * UMMA_M), w_units, idesc0);
+              const int o = r - 2;                       // the output row this source row completes
+              if (o >= 0 && ((o & 7) == 7 || o == n_out - 1)) umma_commit_addr(acc_full_addr + (uint32_t)((o >> 3) & 1) * 8u);
+              if (IS_A) { if (i == 15 || r == n_src - 1) umma_commit_addr(sempty0); }
+              else { if (ii == 7 || r == n_src - 1) umma_commit_addr(sempty0 + (uint32_t)h * 8u); }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    // phantom groups: keep every barrier of the rings in step
+    if (!IS_A) {
+      for (int j = (n_src + CH_RG - 1) / CH_RG; j < nb_src * CH_GPB; ++j) {
+        const uint32_t blk = sb + (uint32_t)(j >> 1);
+        const uint32_t idx = (blk % SRC_BLOCKS) * CH_GPB + (uint32_t)(j & 1);
+        mbar_wait(&src_full[idx], (blk / SRC_BLOCKS) & 1u);
+        if (lane == 0) mbar_arrive(&src_empty[idx]);
+        __syncwarp();
+      }
+    }
+    for (int j = (n_out + CH_RG - 1) / CH_RG; j < nb_out * CH_GPB; ++j) {
+      mbar_wait(&acc_empty[j & 1], (ob + (uint32_t)(j >> 1)) & 1u);
+      if (lane == 0) mbar_arrive(&acc_full[j & 1]);
+      __syncwarp();
+    }
+    sb += (uint32_t)nb_src;
+    ob += (uint32_t)nb_out;
+  }
+}
+
+// Epilogue warps of one layer (8 warps = two warpgroups taking alternate groups of 4 rows).
+//   IS_A: codes -> mid ring (shared memory), out-of-frame positions forced to the pad byte;  else: codes -> global memory.
+template <bool IS_A>
+__device__ __forceinline__ void chain_epilogue(const UmmaParams& P, const ChainGeom& G, const int ew, const int lane,
+                                               const uint32_t tmem_base, uint64_t* const acc_full, uint64_t* const acc_empty,
+                                               uint64_t* const mid_full, uint64_t* const mid_empty, uint8_t* const mid_ring,
+                                               uint4* __restrict__ out) {
+  const int wg = (ew >> 2) & 1;                        // warpgroup within the layer: groups j == wg (mod 2)
+  const int quarter = ew & 3;                          // TMEM lane quarter (== warp % 4)
+  const int ox = quarter * 32 + lane;
+  const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16) + (IS_A ? 0u : (uint32_t)(CH_BLK * CH_NCOLS));
+  const float relu_floor = P.relu ? 0.f : -INFINITY;
+
+  int cinit[1][16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    cinit[0][n] = P.c_init[0][n];
+    asm volatile("" : "+r"(cinit[0][n]));             // keep the constants in registers
+  }
+#pragma unroll
+  for (int i = 0; i < CH_RG; ++i) slot_store<1>(tq + (uint32_t)((wg * CH_RG + i) * CH_NCOLS), cinit);
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&acc_empty[wg]);
+
+  uint32_t ob = 0;                                     // running output block counter of this layer
+  for (int s = blockIdx.x; s < G.num_strips; s += gridDim.x) {
+    const ChainStrip t = chain_strip(G, s);
+    const int n_out = IS_A ? t.sh + 2 : t.sh;
+    const int nb_out = (n_out + CH_BLK - 1) / CH_BLK;
+    // frame coordinates of this lane's column and of output row 0
+    const int fx = IS_A ? t.x0 - 1 + ox : t.x0 + ox;
+    const int fy0 = IS_A ? t.ys - 1 : t.ys;
+    const bool col_ok = IS_A ? (fx >= 0 && fx < G.W) : (ox < G.TW && fx < G.W);
+    uint4* const orow0 = out + ((long long)t.b * G.H + fy0) * G.W + fx;
+    for (int k = 0; k < nb_out; ++k) {
+      const uint32_t blk = ob + (uint32_t)k;
+      const int g = wg;                                  // this warpgroup's half of every block: slots 8 wg .. 8 wg + 7
+      const int j = k * CH_GPB + g;                      // strip-relative group
+      const uint32_t mslot = blk % CH_MID_BLOCKS;
+      const uint32_t midx = mslot * CH_GPB + (uint32_t)g;
+      __syncwarp();
+      mbar_wait(&acc_full[g], blk & 1u);
+      tc_fence_after();
+      if (IS_A) mbar_wait(&mid_empty[midx], ((blk / CH_MID_BLOCKS) & 1u) ^ 1u);
+      if (j * CH_RG < n_out) {
+        const uint32_t taddr0 = tq + (uint32_t)(g * CH_RG * CH_NCOLS);
+        uint4* const mrow = reinterpret_cast<uint4*>(mid_ring + (size_t)mslot * CH_BLK_BYTES) + (g * CH_RG) * UMMA_M + ox;
+        int acc[2][1][16];
+        slot_load<1>(taddr0, acc[0]);
+#pragma unroll
+        for (int i = 0; i < CH_RG; ++i) {
+          const int cur = i & 1;
+          tmem_ld_wait();
+          slot_fence<1>(acc[cur]);
+          if (i + 1 < CH_RG) slot_load<1>(taddr0 + (uint32_t)((i + 1) * CH_NCOLS), acc[(i + 1) & 1]);
+          slot_store<1>(taddr0 + (uint32_t)(i * CH_NCOLS), cinit);
+          uint4 code;
+          epilogue_pixel<1, EPI_PLAIN, 1, 0, 0, false>(P, acc[cur], make_uint4(0u, 0u, 0u, 0u), &code, nullptr, nullptr, 0,
+                                                       relu_floor, true);
+          const int o = j * CH_RG + i;
+          const int fy = fy0 + o;
+          if (IS_A) {
+            // out-of-frame positions are the next layer's zero padding: byte 0 = code -128 (its z_in <= -128)
+            const bool in_frame = col_ok && fy >= 0 && fy < G.H;
+            mrow[i * UMMA_M] = in_frame ? code : make_uint4(0u, 0u, 0u, 0u);
+          } else {
+            if (col_ok && o < n_out) orow0[(long long)o * G.W] = code;
+          }
+        }
+      }
+      if (IS_A) fence_proxy_async();                    // generic-proxy stores -> visible to the UMMA reads of issuer B
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (IS_A) mbar_arrive(&mid_full[midx]);
+        mbar_arrive(&acc_empty[g]);
+      }
+    }
+    ob += (uint32_t)nb_out;
+  }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1)
+conv_chain2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ UmmaParams PA,
+                   const __grid_constant__ UmmaParams PB, const __grid_constant__ ChainGeom G,
+                   const uint8_t* __restrict__ w_a, const uint8_t* __restrict__ w_b, uint4* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* const in_ring = smem;
+  uint8_t* const mid_ring = in_ring + CH_IN_BLOCKS * CH_BLK_BYTES;
+  uint8_t* const w_s = mid_ring + CH_MID_BLOCKS * CH_BLK_BYTES;          // [2][CH_W_BYTES]; also absorbs the 32-byte
+                                                                          // over-read of the mid ring's last row
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(w_s + 2 * CH_W_BYTES);
+  uint64_t* const in_full = bars;                                         // [CH_IN_BLOCKS]
+  uint64_t* const in_empty = in_full + CH_IN_BLOCKS;                      // [CH_IN_BLOCKS]
+  uint64_t* const acc_full_a = in_empty + CH_IN_BLOCKS;                   // [CH_GPB]
+  uint64_t* const acc_empty_a = acc_full_a + CH_GPB;
+  uint64_t* const acc_full_b = acc_empty_a + CH_GPB;
+  uint64_t* const acc_empty_b = acc_full_b + CH_GPB;
+  uint64_t* const mid_full = acc_empty_b + CH_GPB;                        // [CH_MID_BLOCKS * CH_GPB]
+  uint64_t* const mid_empty = mid_full + CH_MID_BLOCKS * CH_GPB;
+  uint32_t* const tmem_base_s = reinterpret_cast<uint32_t*>(mid_empty + CH_MID_BLOCKS * CH_GPB);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- one-time setup ----
+  for (uint32_t i = threadIdx.x; i < CH_W_BYTES / 16; i += blockDim.x) {
+    reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(w_a) + i);
+    reinterpret_cast<uint4*>(w_s + CH_W_BYTES)[i] = __ldg(reinterpret_cast<const uint4*>(w_b) + i);
+  }
+  fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+    for (int i = 0; i < CH_IN_BLOCKS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
+    for (int i = 0; i < CH_GPB; ++i) {
+      mbar_init(&acc_full_a[i], 1); mbar_init(&acc_empty_a[i], 4);
+      mbar_init(&acc_full_b[i], 1); mbar_init(&acc_empty_b[i], 4);
+    }
+    for (int i = 0; i < CH_MID_BLOCKS * CH_GPB; ++i) { mbar_init(&mid_full[i], 4); mbar_init(&mid_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_s, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t ib = 0;                                   // running input block counter
+      for (int s = blockIdx.x; s < G.num_strips; s += gridDim.x) {
+        const ChainStrip t = chain_strip(G, s);
+        const int nb_in = (t.sh + 4 + CH_BLK - 1) / CH_BLK;
+        for (int k = 0; k < nb_in; ++k, ++ib) {
+          const uint32_t slot = ib % CH_IN_BLOCKS;
+          mbar_wait(&in_empty[slot], ((ib / CH_IN_BLOCKS) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&in_full[slot], CH_BLK_BYTES);
+          tma_load_3d(in_ring + (size_t)slot * CH_BLK_BYTES, &tmap, (t.x0 - 2) * 2, t.ys - 2 + k * CH_BLK, t.b, &in_full[slot]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    chain_issuer<true>(G, lane, tmem_base, w_s, in_ring, in_full, in_empty, acc_full_a, acc_empty_a);
+  } else if (warp == 2) {
+    chain_issuer<false>(G, lane, tmem_base, w_s + CH_W_BYTES, mid_ring, mid_full, mid_empty, acc_full_b, acc_empty_b);
+  } else if (warp >= 4) {
+    // ================= epilogues: warps 4-11 layer A (-> mid ring), warps 12-19 layer B (-> global memory) =================
+    const int ew = warp - 4;
+    if (ew < CH_EPI_WARPS) chain_epilogue<true>(PA, G, ew, lane, tmem_base, acc_full_a, acc_empty_a, mid_full, mid_empty, mid_ring, out);
+    else chain_epilogue<false>(PB, G, ew, lane, tmem_base, acc_full_b, acc_empty_b, mid_full, mid_empty, mid_ring, out);
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+bool chain2_supported(const LayerDev& A, const LayerDev& B) {
+  const LayerConst& a = A.c;
+  const LayerConst& b = B.c;
+  auto plain3 = [](const LayerDev& L) {
+    const LayerConst& c = L.c;
+    return L.impl == SESRQ_IMPL_UMMA && L.umma_n == 16 && c.k == 3 && c.cin == 16 && c.cout == 16 && c.epi == EPI_PLAIN &&
+           c.first_layer == 0 && c.pad_byte == 0 && c.save_rc == 0 && !needs_floor(c);
+  };
+  (void)a; (void)b;
+  return plain3(A) && plain3(B);
+}
+
+int launch_conv_chain2(const LayerDev& A, const LayerDev& Bl, const uint8_t* d_in, uint8_t* d_out, int B, int H, int W,
+                       cudaStream_t st) {
+  if (!chain2_supported(A, Bl)) return SESRQ_EUNSUPPORTED;
+  if (!d_in || !d_out) return SESRQ_EINVAL;
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return SESRQ_EUNSUPPORTED;
+  UmmaParams PA, PB;
+  memset(&PA, 0, sizeof(PA));
+  memset(&PB, 0, sizeof(PB));
+  fill_epilogue_params(PA, A.c, 1);
+  fill_epilogue_params(PB, Bl.c, 1);
+  ChainGeom G;
+  memset(&G, 0, sizeof(G));
+  G.B = B; G.H = H; G.W = W;
+  G.tiles_x = cdiv(W, UMMA_M - 4);
+  G.TW = cdiv(W, G.tiles_x);
+  const int sms = sm_count();
+  // Segments per frame column: a strip pays ~8 rows of fill / drain and halo recomputation; the static round-robin
+  // schedule costs ceil(strips / CTAs) strips on the busiest CTA.  Pick the split with the smallest modelled time.
+  const long long cols = (long long)B * G.tiles_x;
+  int best_nseg = 1;
+  double best_cost = 1e300;
+  for (int nseg = 1; nseg <= std::max(1, H / 32); ++nseg) {
+    const int SH = cdiv(H, nseg);
+    if ((long long)SH * nseg - H >= SH) continue;        // an empty last segment
+    const long long strips = cols * nseg;
+    const double cost = (double)((strips + sms - 1) / sms) * (SH + 8);
+    if (cost < best_cost) { best_cost = cost; best_nseg = nseg; }
+  }
+  G.nseg = best_nseg;
+  G.SH = cdiv(H, G.nseg);
+  G.num_strips = (int)(cols * G.nseg);
+  G.idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(UMMA_M >> 4) << 24);
+
+  CUtensorMap tmap;
+  cuuint64_t gdim[3] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  cuuint32_t box[3] = {(cuuint32_t)UMMA_M * 2, (cuuint32_t)CH_BLK, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t*>(d_in), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (chain)");
+    return SESRQ_ECUDA;
+  }
+  const size_t smem = (size_t)(CH_IN_BLOCKS + CH_MID_BLOCKS) * CH_BLK_BYTES + 2 * CH_W_BYTES +
+                      8 * (2 * CH_IN_BLOCKS + 4 * CH_GPB + 2 * CH_MID_BLOCKS * CH_GPB) + 64;
+  static std::atomic<uint64_t> optin_done{0};
+  if (int rc = ensure_smem_optin(conv_chain2_kernel, 227 * 1024, optin_done)) return rc;
+  const int grid = std::min(G.num_strips, sms);
+  conv_chain2_kernel<<<grid, CH_THREADS, smem, st>>>(tmap, PA, PB, G, A.d_wumma, Bl.d_wumma, reinterpret_cast<uint4*>(d_out));
+  SESRQ_LAUNCH_CHECK("conv_chain2_kernel");
+  return SESRQ_OK;
+}
+
+}  // namespace sesrq
