@@ -33,17 +33,23 @@
 namespace sesrq {
 
 constexpr int CH_BLK = 16;                              // rows per ring block = accumulator slots per layer
-constexpr int CH_RG = 8;                                // rows per group (half a block: one epilogue warpgroup each)
-constexpr int CH_GPB = CH_BLK / CH_RG;                  // groups per block
+constexpr int CH_HALF = 8;                              // rows per issue step / per source group of the mid ring
+constexpr int CH_HPB = CH_BLK / CH_HALF;                // halves per block
+constexpr int CH_RG = 4;                                // rows per accumulator group (completion / re-arm signalling)
+constexpr int CH_GPB = CH_BLK / CH_RG;                  // accumulator groups per block
 constexpr int CH_IN_BLOCKS = 3;                         // input ring: 3 x 32 KB
 constexpr int CH_MID_BLOCKS = 2;                        // mid ring:   2 x 32 KB
 constexpr uint32_t CH_ROW_BYTES = UMMA_M * 16;          // one 128-pixel row of NHWC16
 constexpr uint32_t CH_BLK_BYTES = CH_BLK * CH_ROW_BYTES;
-constexpr int CH_EPI_WARPS = 8;                         // per layer: two warpgroups, alternating groups
+constexpr int CH_EPI_WARPS = 8;                         // per layer: two warpgroups, each takes 2 rows of every 4-row group
+constexpr int CH_WROWS = CH_RG / (CH_EPI_WARPS / 4);    // rows of a group per warpgroup
 constexpr int CH_THREADS = (4 + 2 * CH_EPI_WARPS) * 32;
 constexpr int CH_NCOLS = 16;                            // accumulator columns per row slot (NS = 1)
 constexpr int CH_NTOT = 3 * CH_NCOLS;                   // B image rows per K half (3 vertical taps)
 constexpr uint32_t CH_W_BYTES = 2 * 2 * CH_NTOT * 16;   // 2 tap pairs x 2 K halves
+constexpr int CH_CTOT = 4 * CH_NCOLS;                   // rows per K half of the row-pair image (4 output rows)
+constexpr uint32_t CH_C_BYTES = 2 * CH_CTOT * 16;       // row-pair image of the third horizontal tap (see chain_issuer)
+constexpr uint32_t CH_WL_BYTES = CH_W_BYTES + CH_C_BYTES;   // shared-memory weights of one layer
 
 struct ChainGeom {
   int32_t B, H, W, TW, tiles_x, nseg, SH, num_strips;
@@ -99,12 +105,34 @@ __device__ __forceinline__ void chain_mma_pair(const uint32_t d_base, const uint
             make_desc((w_units + (uint32_t)(q * 2 * CH_NTOT + jblk * CH_NCOLS)) | b_lbo, desc_hi), idesc, 1u);
 }
 
-// The warp waits (lane 0: source barrier, lane 1: accumulator barrier, both polled in the same instruction) until the
-// source rows of a half block are present and the row slots it touches first are drained and re-armed.
-__device__ __forceinline__ void chain_wait2(const int lane, const bool need_src, const uint32_t bar_src, const uint32_t par_src,
-                                            const bool need_acc, const uint32_t bar_acc, const uint32_t par_acc) {
-  const bool mine = (lane == 0 && need_src) || (lane == 1 && need_acc);
-  const uint32_t bar = lane == 0 ? bar_src : bar_acc;
+// The third horizontal tap (dx = 2) of TWO consecutive source rows in one MMA: K chunk 0 = pixel x+2 of row r, chunk 1 =
+// pixel x+2 of row r+1 (A descriptor LBO = one row), N = up to 64 = output rows r-2 .. r+1.  The row-pair B image holds,
+// per K half, four row blocks: half 0 = W[dy = 2, 1, 0][dx = 2], 0;  half 1 = 0, W[dy = 2, 1, 0][dx = 2].  With the two
+// dx = (0, 1) MMAs of the rows this makes 3 MMAs per row pair instead of 4: the second tap pair of the per-row scheme
+// multiplies zeros in half of its K, and the A stream from shared memory (4 KB per MMA) is what bounds this kernel.
+__device__ __forceinline__ void chain_mma_c(const uint32_t d_base, const uint32_t a_row_lo_pairlbo, const uint32_t c_units,
+                                            const uint32_t idesc, const int slot, const int cblk) {
+  const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t b_lbo = (uint32_t)CH_CTOT << 16;
+  umma_i8(d_base + (uint32_t)(slot * CH_NCOLS), make_desc(a_row_lo_pairlbo + 2u, desc_hi),
+          make_desc((c_units + (uint32_t)(cblk * CH_NCOLS)) | b_lbo, desc_hi), idesc, 1u);
+}
+// dx = (0, 1) of one source row (first tap pair of the per-row image)
+__device__ __forceinline__ void chain_mma_a(const uint32_t d_base, const uint32_t a_row_lo, const uint32_t w_units,
+                                            const uint32_t idesc, const int slot, const int jblk) {
+  const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t b_lbo = (uint32_t)CH_NTOT << 16;
+  umma_i8(d_base + (uint32_t)(slot * CH_NCOLS), make_desc(a_row_lo, desc_hi),
+          make_desc((w_units + (uint32_t)(jblk * CH_NCOLS)) | b_lbo, desc_hi), idesc, 1u);
+}
+
+// The warp waits until the source rows of a half block are present (lane 0) and the two accumulator groups whose row
+// slots it touches first are drained and re-armed (lanes 1, 2); the three barriers are polled by the same instruction.
+__device__ __forceinline__ void chain_wait3(const int lane, const bool need_src, const uint32_t bar_src, const uint32_t par_src,
+                                            const bool need_acc0, const bool need_acc1, const uint32_t bar_acc0,
+                                            const uint32_t par_acc) {
+  const bool mine = (lane == 0 && need_src) || (lane == 1 && need_acc0) || (lane == 2 && need_acc1);
+  const uint32_t bar = lane == 0 ? bar_src : bar_acc0 + (lane == 2 ? 8u : 0u);
   const uint32_t par = lane == 0 ? par_src : par_acc;
   uint32_t ok;
   do {
@@ -137,6 +165,8 @@ __device__ __forceinline__ void chain_issuer(const ChainGeom& G, const int lane,
   const uint32_t idesc1 = idesc0 | ((uint32_t)((1 * CH_NCOLS) >> 3) << 17);
   const uint32_t idesc2 = idesc0 | ((uint32_t)((2 * CH_NCOLS) >> 3) << 17);
   const uint32_t idesc3 = idesc0 | ((uint32_t)((3 * CH_NCOLS) >> 3) << 17);
+  const uint32_t idesc4 = idesc0 | ((uint32_t)((4 * CH_NCOLS) >> 3) << 17);
+  const uint32_t c_units = w_units + (CH_W_BYTES >> 4);
   const uint32_t acc_full_addr = smem_u32(acc_full), acc_empty_addr = smem_u32(acc_empty);
   const uint32_t src_full_addr = smem_u32(src_full), src_empty_addr = smem_u32(src_empty);
   uint32_t sb = 0;                                       // running source block counter (input blocks / mid blocks)
@@ -155,31 +185,37 @@ __device__ __forceinline__ void chain_issuer(const ChainGeom& G, const int lane,
       const uint32_t opar = (ob + (uint32_t)k) & 1u;
       const uint32_t a_blk = (src_units + sslot * (CH_BLK * UMMA_M)) | (1u << 16);
       // barrier addresses of the two halves
-      const uint32_t sfull0 = src_full_addr + (IS_A ? sslot : sslot * CH_GPB) * 8u;
-      const uint32_t sempty0 = src_empty_addr + (IS_A ? sslot : sslot * CH_GPB) * 8u;
+      const uint32_t sfull0 = src_full_addr + (IS_A ? sslot : sslot * CH_HPB) * 8u;
+      const uint32_t sempty0 = src_empty_addr + (IS_A ? sslot : sslot * CH_HPB) * 8u;
       if (k >= 1 && r0 + CH_BLK - 1 <= n_out - 1) {
         // ---------------- interior block ----------------
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          chain_wait2(lane, IS_A ? (h == 0) : true, sfull0 + (IS_A ? 0u : (uint32_t)h * 8u), spar, true,
-                      acc_empty_addr + (uint32_t)h * 8u, opar);
+          chain_wait3(lane, IS_A ? (h == 0) : true, sfull0 + (IS_A ? 0u : (uint32_t)h * 8u), spar, true, true,
+                      acc_empty_addr + (uint32_t)(2 * h) * 8u, opar);
           if (elect_one()) {
 #pragma unroll
-            for (int ii = 0; ii < CH_RG; ++ii) {
-              const int i = h * CH_RG + ii;              // row within the block: output rows r-2 .. r = slots (i-2 .. i) mod 16
-              const uint32_t a_row = a_blk + (uint32_t)(i * UMMA_M);
+            for (int pp = 0; pp < CH_HALF / 2; ++pp) {
+              const int i = h * CH_HALF + 2 * pp;          // first row of the pair: output rows r-2 .. r+1 = slots (i-2 .. i+1) mod 16
+              const uint32_t a_row0 = a_blk + (uint32_t)(i * UMMA_M);
+              const uint32_t a_row1 = a_row0 + (uint32_t)UMMA_M;
+              const uint32_t a_pair = (a_row0 & 0xFFFFu) | ((uint32_t)UMMA_M << 16);   // LBO = one row
               if (i >= 2) {
-                chain_mma_pair(d_base, a_row, w_units, idesc3, i - 2, 0);
-              } else if (i == 1) {
-                chain_mma_pair(d_base, a_row, w_units, idesc1, 15, 0);
-                chain_mma_pair(d_base, a_row, w_units, idesc2, 0, 1);
-              } else {
-                chain_mma_pair(d_base, a_row, w_units, idesc2, 14, 0);
-                chain_mma_pair(d_base, a_row, w_units, idesc1, 0, 2);
+                chain_mma_a(d_base, a_row0, w_units, idesc3, i - 2, 0);
+                chain_mma_a(d_base, a_row1, w_units, idesc3, i - 1, 0);
+                chain_mma_c(d_base, a_pair, c_units, idesc4, i - 2, 0);
+              } else {                                   // the slot ring wraps inside this pair (slots 14, 15, 0, 1)
+                chain_mma_a(d_base, a_row0, w_units, idesc2, 14, 0);
+                chain_mma_a(d_base, a_row0, w_units, idesc1, 0, 2);
+                chain_mma_a(d_base, a_row1, w_units, idesc1, 15, 0);
+                chain_mma_a(d_base, a_row1, w_units, idesc2, 0, 1);
+                chain_mma_c(d_base, a_pair, c_units, idesc2, 14, 0);
+                chain_mma_c(d_base, a_pair, c_units, idesc2, 0, 2);
               }
-              if (ii == 1) umma_commit_addr(acc_full_addr + (uint32_t)(1 - h) * 8u);     // output row r-2 closes the other half's group
-              if (IS_A) { if (i == 15) umma_commit_addr(sempty0); }
-              else { if (ii == 7) umma_commit_addr(sempty0 + (uint32_t)h * 8u); }
+              // output row r + 1 - 2 = i - 1 closes a 4-row group when (i - 1) % 4 == 3: pairs i = 0, 4, 8, 12
+              if ((i & 3) == 0) umma_commit_addr(acc_full_addr + (uint32_t)(((i + 12) & 15) >> 2) * 8u);
+              if (IS_A) { if (i == 14) umma_commit_addr(sempty0); }
+              else { if (pp == CH_HALF / 2 - 1) umma_commit_addr(sempty0 + (uint32_t)h * 8u); }
             }
           }
           __syncwarp();
@@ -188,19 +224,19 @@ __device__ __forceinline__ void chain_issuer(const ChainGeom& G, const int lane,
         // ---------------- edge block (first / last of a strip): rolled, everything decided at run time ----------------
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
-          const int rh = r0 + h * CH_RG;
+          const int rh = r0 + h * CH_HALF;
           if (rh >= n_src) break;
-          chain_wait2(lane, IS_A ? (h == 0) : true, sfull0 + (IS_A ? 0u : (uint32_t)h * 8u), spar, rh < n_out,
-                      acc_empty_addr + (uint32_t)h * 8u, opar);
+          chain_wait3(lane, IS_A ? (h == 0) : true, sfull0 + (IS_A ? 0u : (uint32_t)h * 8u), spar, rh < n_out, rh + CH_RG < n_out,
+                      acc_empty_addr + (uint32_t)(2 * h) * 8u, opar);
           if (elect_one()) {
 #pragma unroll 1
-            for (int ii = 0; ii < CH_RG; ++ii) {
-              const int i = h * CH_RG + ii;
+            for (int ii = 0; ii < CH_HALF; ++ii) {
+              const int i = h * CH_HALF + ii;
               const int r = r0 + i;
               if (r >= n_src) break;
               chain_issue_row(r, n_out, d_base, a_blk + (uint32_t)(i * UMMA_M), w_units, idesc0);
               const int o = r - 2;                       // the output row this source row completes
-              if (o >= 0 && ((o & 7) == 7 || o == n_out - 1)) umma_commit_addr(acc_full_addr + (uint32_t)((o >> 3) & 1) * 8u);
+              if (o >= 0 && ((o & 3) == 3 || o == n_out - 1)) umma_commit_addr(acc_full_addr + (uint32_t)((o >> 2) & 3) * 8u);
               if (IS_A) { if (i == 15 || r == n_src - 1) umma_commit_addr(sempty0); }
               else { if (ii == 7 || r == n_src - 1) umma_commit_addr(sempty0 + (uint32_t)h * 8u); }
             }
@@ -211,17 +247,17 @@ __device__ __forceinline__ void chain_issuer(const ChainGeom& G, const int lane,
     }
     // phantom groups: keep every barrier of the rings in step
     if (!IS_A) {
-      for (int j = (n_src + CH_RG - 1) / CH_RG; j < nb_src * CH_GPB; ++j) {
+      for (int j = (n_src + CH_HALF - 1) / CH_HALF; j < nb_src * CH_HPB; ++j) {
         const uint32_t blk = sb + (uint32_t)(j >> 1);
-        const uint32_t idx = (blk % SRC_BLOCKS) * CH_GPB + (uint32_t)(j & 1);
+        const uint32_t idx = (blk % SRC_BLOCKS) * CH_HPB + (uint32_t)(j & 1);
         mbar_wait(&src_full[idx], (blk / SRC_BLOCKS) & 1u);
         if (lane == 0) mbar_arrive(&src_empty[idx]);
         __syncwarp();
       }
     }
     for (int j = (n_out + CH_RG - 1) / CH_RG; j < nb_out * CH_GPB; ++j) {
-      mbar_wait(&acc_empty[j & 1], (ob + (uint32_t)(j >> 1)) & 1u);
-      if (lane == 0) mbar_arrive(&acc_full[j & 1]);
+      mbar_wait(&acc_empty[j & 3], (ob + (uint32_t)(j >> 2)) & 1u);
+      if (lane == 0) mbar_arrive(&acc_full[j & 3]);
       __syncwarp();
     }
     sb += (uint32_t)nb_src;
@@ -236,7 +272,7 @@ __device__ __forceinline__ void chain_epilogue(const UmmaParams& P, const ChainG
                                                const uint32_t tmem_base, uint64_t* const acc_full, uint64_t* const acc_empty,
                                                uint64_t* const mid_full, uint64_t* const mid_empty, uint8_t* const mid_ring,
                                                uint4* __restrict__ out) {
-  const int wg = (ew >> 2) & 1;                        // warpgroup within the layer: groups j == wg (mod 2)
+  const int wg = (ew >> 2) % (CH_EPI_WARPS / 4);       // warpgroup within the layer
   const int quarter = ew & 3;                          // TMEM lane quarter (== warp % 4)
   const int ox = quarter * 32 + lane;
   const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16) + (IS_A ? 0u : (uint32_t)(CH_BLK * CH_NCOLS));
@@ -249,11 +285,14 @@ __device__ __forceinline__ void chain_epilogue(const UmmaParams& P, const ChainG
     asm volatile("" : "+r"(cinit[0][n]));             // keep the constants in registers
   }
 #pragma unroll
-  for (int i = 0; i < CH_RG; ++i) slot_store<1>(tq + (uint32_t)((wg * CH_RG + i) * CH_NCOLS), cinit);
+  for (int g = 0; g < CH_GPB; ++g)
+#pragma unroll
+    for (int i = 0; i < CH_WROWS; ++i) slot_store<1>(tq + (uint32_t)((g * CH_RG + wg * CH_WROWS + i) * CH_NCOLS), cinit);
   tmem_st_wait();
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(&acc_empty[wg]);
+  if (lane == 0)
+    for (int g = 0; g < CH_GPB; ++g) mbar_arrive(&acc_empty[g]);
 
   uint32_t ob = 0;                                     // running output block counter of this layer
   for (int s = blockIdx.x; s < G.num_strips; s += gridDim.x) {
@@ -267,47 +306,50 @@ __device__ __forceinline__ void chain_epilogue(const UmmaParams& P, const ChainG
     uint4* const orow0 = out + ((long long)t.b * G.H + fy0) * G.W + fx;
     for (int k = 0; k < nb_out; ++k) {
       const uint32_t blk = ob + (uint32_t)k;
-      const int g = wg;                                  // this warpgroup's half of every block: slots 8 wg .. 8 wg + 7
-      const int j = k * CH_GPB + g;                      // strip-relative group
       const uint32_t mslot = blk % CH_MID_BLOCKS;
-      const uint32_t midx = mslot * CH_GPB + (uint32_t)g;
-      __syncwarp();
-      mbar_wait(&acc_full[g], blk & 1u);
-      tc_fence_after();
-      if (IS_A) mbar_wait(&mid_empty[midx], ((blk / CH_MID_BLOCKS) & 1u) ^ 1u);
-      if (j * CH_RG < n_out) {
-        const uint32_t taddr0 = tq + (uint32_t)(g * CH_RG * CH_NCOLS);
-        uint4* const mrow = reinterpret_cast<uint4*>(mid_ring + (size_t)mslot * CH_BLK_BYTES) + (g * CH_RG) * UMMA_M + ox;
-        int acc[2][1][16];
-        slot_load<1>(taddr0, acc[0]);
+#pragma unroll 1
+      for (int g = 0; g < CH_GPB; ++g) {                 // both warpgroups share every 4-row group: 2 rows each
+        const uint32_t midx = mslot * CH_HPB + (uint32_t)(g >> 1);        // mid ring barriers: one pair per 8 rows
+        const int row0 = g * CH_RG + wg * CH_WROWS;      // first of this warpgroup's rows within the block (= slot number)
+        const int o0 = k * CH_BLK + row0;                // strip-relative output row
+        __syncwarp();
+        mbar_wait(&acc_full[g], blk & 1u);
+        tc_fence_after();
+        if (IS_A) mbar_wait(&mid_empty[midx], ((blk / CH_MID_BLOCKS) & 1u) ^ 1u);
+        if (o0 < n_out) {
+          const uint32_t taddr0 = tq + (uint32_t)(row0 * CH_NCOLS);
+          uint4* const mrow = reinterpret_cast<uint4*>(mid_ring + (size_t)mslot * CH_BLK_BYTES) + row0 * UMMA_M + ox;
+          int acc[2][1][16];
+          slot_load<1>(taddr0, acc[0]);
 #pragma unroll
-        for (int i = 0; i < CH_RG; ++i) {
-          const int cur = i & 1;
-          tmem_ld_wait();
-          slot_fence<1>(acc[cur]);
-          if (i + 1 < CH_RG) slot_load<1>(taddr0 + (uint32_t)((i + 1) * CH_NCOLS), acc[(i + 1) & 1]);
-          slot_store<1>(taddr0 + (uint32_t)(i * CH_NCOLS), cinit);
-          uint4 code;
-          epilogue_pixel<1, EPI_PLAIN, 1, 0, 0, false>(P, acc[cur], make_uint4(0u, 0u, 0u, 0u), &code, nullptr, nullptr, 0,
-                                                       relu_floor, true);
-          const int o = j * CH_RG + i;
-          const int fy = fy0 + o;
-          if (IS_A) {
-            // out-of-frame positions are the next layer's zero padding: byte 0 = code -128 (its z_in <= -128)
-            const bool in_frame = col_ok && fy >= 0 && fy < G.H;
-            mrow[i * UMMA_M] = in_frame ? code : make_uint4(0u, 0u, 0u, 0u);
-          } else {
-            if (col_ok && o < n_out) orow0[(long long)o * G.W] = code;
+          for (int i = 0; i < CH_WROWS; ++i) {
+            const int cur = i & 1;
+            tmem_ld_wait();
+            slot_fence<1>(acc[cur]);
+            if (i + 1 < CH_WROWS) slot_load<1>(taddr0 + (uint32_t)((i + 1) * CH_NCOLS), acc[(i + 1) & 1]);
+            slot_store<1>(taddr0 + (uint32_t)(i * CH_NCOLS), cinit);
+            uint4 code;
+            epilogue_pixel<1, EPI_PLAIN, 1, 0, 0, false>(P, acc[cur], make_uint4(0u, 0u, 0u, 0u), &code, nullptr, nullptr, 0,
+                                                         relu_floor, true);
+            const int o = o0 + i;
+            const int fy = fy0 + o;
+            if (IS_A) {
+              // out-of-frame positions are the next layer's zero padding: byte 0 = code -128 (its z_in <= -128)
+              const bool in_frame = col_ok && fy >= 0 && fy < G.H;
+              mrow[i * UMMA_M] = in_frame ? code : make_uint4(0u, 0u, 0u, 0u);
+            } else {
+              if (col_ok && o < n_out) orow0[(long long)o * G.W] = code;
+            }
           }
         }
-      }
-      if (IS_A) fence_proxy_async();                    // generic-proxy stores -> visible to the UMMA reads of issuer B
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (IS_A) mbar_arrive(&mid_full[midx]);
-        mbar_arrive(&acc_empty[g]);
+        if (IS_A) fence_proxy_async();                  // generic-proxy stores -> visible to the UMMA reads of issuer B
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (IS_A) mbar_arrive(&mid_full[midx]);
+          mbar_arrive(&acc_empty[g]);
+        }
       }
     }
     ob += (uint32_t)nb_out;
@@ -323,16 +365,16 @@ conv_chain2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   uint8_t* const mid_ring = in_ring + CH_IN_BLOCKS * CH_BLK_BYTES;
   uint8_t* const w_s = mid_ring + CH_MID_BLOCKS * CH_BLK_BYTES;          // [2][CH_W_BYTES]; also absorbs the 32-byte
                                                                           // over-read of the mid ring's last row
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(w_s + 2 * CH_W_BYTES);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(w_s + 2 * CH_WL_BYTES);
   uint64_t* const in_full = bars;                                         // [CH_IN_BLOCKS]
   uint64_t* const in_empty = in_full + CH_IN_BLOCKS;                      // [CH_IN_BLOCKS]
   uint64_t* const acc_full_a = in_empty + CH_IN_BLOCKS;                   // [CH_GPB]
   uint64_t* const acc_empty_a = acc_full_a + CH_GPB;
   uint64_t* const acc_full_b = acc_empty_a + CH_GPB;
   uint64_t* const acc_empty_b = acc_full_b + CH_GPB;
-  uint64_t* const mid_full = acc_empty_b + CH_GPB;                        // [CH_MID_BLOCKS * CH_GPB]
-  uint64_t* const mid_empty = mid_full + CH_MID_BLOCKS * CH_GPB;
-  uint32_t* const tmem_base_s = reinterpret_cast<uint32_t*>(mid_empty + CH_MID_BLOCKS * CH_GPB);
+  uint64_t* const mid_full = acc_empty_b + CH_GPB;                        // [CH_MID_BLOCKS * CH_HPB]
+  uint64_t* const mid_empty = mid_full + CH_MID_BLOCKS * CH_HPB;
+  uint32_t* const tmem_base_s = reinterpret_cast<uint32_t*>(mid_empty + CH_MID_BLOCKS * CH_HPB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -340,17 +382,27 @@ conv_chain2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   // ---- one-time setup ----
   for (uint32_t i = threadIdx.x; i < CH_W_BYTES / 16; i += blockDim.x) {
     reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(w_a) + i);
-    reinterpret_cast<uint4*>(w_s + CH_W_BYTES)[i] = __ldg(reinterpret_cast<const uint4*>(w_b) + i);
+    reinterpret_cast<uint4*>(w_s + CH_WL_BYTES)[i] = __ldg(reinterpret_cast<const uint4*>(w_b) + i);
+  }
+  // row-pair image of the third horizontal tap, from the per-row image's block (pair 1, K half 0) = W[dy = 2, 1, 0][dx = 2]
+  for (uint32_t i = threadIdx.x; i < 2 * CH_C_BYTES / 16; i += blockDim.x) {
+    const uint32_t layer = i / (CH_C_BYTES / 16), e = i % (CH_C_BYTES / 16);
+    const uint32_t half = e / CH_CTOT, row = e % CH_CTOT;                       // row = output row block * 16 + column
+    const int src_row = (int)row - (int)half * CH_NCOLS;                        // half 1 is shifted down by one row block
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (src_row >= 0 && src_row < CH_NTOT)
+      v = __ldg(reinterpret_cast<const uint4*>(layer ? w_b : w_a) + (2 * CH_NTOT) + src_row);   // pair 1, half 0
+    reinterpret_cast<uint4*>(w_s + layer * CH_WL_BYTES + CH_W_BYTES)[e] = v;
   }
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
     for (int i = 0; i < CH_IN_BLOCKS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
     for (int i = 0; i < CH_GPB; ++i) {
-      mbar_init(&acc_full_a[i], 1); mbar_init(&acc_empty_a[i], 4);
-      mbar_init(&acc_full_b[i], 1); mbar_init(&acc_empty_b[i], 4);
+      mbar_init(&acc_full_a[i], 1); mbar_init(&acc_empty_a[i], CH_EPI_WARPS);
+      mbar_init(&acc_full_b[i], 1); mbar_init(&acc_empty_b[i], CH_EPI_WARPS);
     }
-    for (int i = 0; i < CH_MID_BLOCKS * CH_GPB; ++i) { mbar_init(&mid_full[i], 4); mbar_init(&mid_empty[i], 1); }
+    for (int i = 0; i < CH_MID_BLOCKS * CH_HPB; ++i) { mbar_init(&mid_full[i], 2 * CH_EPI_WARPS); mbar_init(&mid_empty[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_base_s, TMEM_COLS);
@@ -377,7 +429,7 @@ conv_chain2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   } else if (warp == 1) {
     chain_issuer<true>(G, lane, tmem_base, w_s, in_ring, in_full, in_empty, acc_full_a, acc_empty_a);
   } else if (warp == 2) {
-    chain_issuer<false>(G, lane, tmem_base, w_s + CH_W_BYTES, mid_ring, mid_full, mid_empty, acc_full_b, acc_empty_b);
+    chain_issuer<false>(G, lane, tmem_base, w_s + CH_WL_BYTES, mid_ring, mid_full, mid_empty, acc_full_b, acc_empty_b);
   } else if (warp >= 4) {
     // ================= epilogues: warps 4-11 layer A (-> mid ring), warps 12-19 layer B (-> global memory) =================
     const int ew = warp - 4;
@@ -455,8 +507,8 @@ int launch_conv_chain2(const LayerDev& A, const LayerDev& Bl, const uint8_t* d_i
     set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (chain)");
     return SESRQ_ECUDA;
   }
-  const size_t smem = (size_t)(CH_IN_BLOCKS + CH_MID_BLOCKS) * CH_BLK_BYTES + 2 * CH_W_BYTES +
-                      8 * (2 * CH_IN_BLOCKS + 4 * CH_GPB + 2 * CH_MID_BLOCKS * CH_GPB) + 64;
+  const size_t smem = (size_t)(CH_IN_BLOCKS + CH_MID_BLOCKS) * CH_BLK_BYTES + 2 * CH_WL_BYTES +
+                      8 * (2 * CH_IN_BLOCKS + 4 * CH_GPB + 2 * CH_MID_BLOCKS * CH_HPB) + 64;
   static std::atomic<uint64_t> optin_done{0};
   if (int rc = ensure_smem_optin(conv_chain2_kernel, 227 * 1024, optin_done)) return rc;
   const int grid = std::min(G.num_strips, sms);
