@@ -99,6 +99,15 @@ void sesrq_net_destroy(SesrqNet* net);
  * weight-norm bound proved the PE clamps inert for it */
 int sesrq_net_layer_info(const SesrqNet* net, int layer, int32_t* impl, int32_t* pe_exact);
 
+/* Layer fusion.  When residual_block.0 and residual_block.1 (layers 1, 2: plain 3x3, 16 -> 16 channels, no PE clamp that
+ * can fire) both run on the tcgen05 path, sesrq_net_forward_i8 executes them in ONE launch and hands the intermediate
+ * codes (the reference's input.2.pt) from the first to the second through shared memory -- they never reach HBM
+ * (csrc/sesrq_chain.cu).  Results are bit-identical either way.  Enabled by default (SESRQ_FUSE=0 in the environment
+ * at create time disables it); sesrq_net_set_fusion switches it per handle and returns the previous setting (0 / 1)
+ * or a negative error code.  With fusion on, sesrq_ws_read_act_i8(domain 2) returns SESRQ_EUNSUPPORTED. */
+int sesrq_net_set_fusion(SesrqNet* net, int enable);
+int sesrq_net_fused_layers(const SesrqNet* net);   /* 1 if the next forward will fuse layers 1 + 2, else 0 */
+
 /* Bytes of device workspace needed by sesrq_net_forward_i8 for a [B,Cin,H,W] batch. */
 size_t sesrq_ws_bytes(const SesrqNet* net, int B, int H, int W);
 

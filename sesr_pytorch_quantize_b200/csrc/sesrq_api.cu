@@ -60,7 +60,7 @@ struct SesrqNet {
   std::vector<int8_t> h_w[SESRQ_NUM_LAYERS];
   bool need_rc = false;       // z_1 != -128: shortcut codes differ from q_1 (quan_func.py:250 vs :280)
   bool need_a0 = false;       // layer 0 runs on the generic path -> separate input-quantise pass
-  bool fuse12 = false;        // layers 1 + 2 in one launch (sesrq_chain.cu); domain 2 is then never materialised
+  bool fuse12 = true;         // layers 1 + 2 in one launch (sesrq_chain.cu); domain 2 is then never materialised
   int device = 0;
   size_t chunk_bytes = (size_t)2048 << 20;   // activation workspace per pass (SESRQ_CHUNK_MB, read at create)
   int host_chunk = 0;                        // frames per host-pipeline chunk (SESRQ_HOST_CHUNK, read at create; 0 = auto)
@@ -304,6 +304,17 @@ int sesrq_net_layer_info(const SesrqNet* net, int layer, int32_t* impl, int32_t*
   return SESRQ_OK;
 }
 
+int sesrq_net_set_fusion(SesrqNet* net, int enable) {
+  if (!net) return -SESRQ_EINVAL;
+  const int prev = net->fuse12 ? 1 : 0;
+  net->fuse12 = enable != 0;
+  return prev;
+}
+
+int sesrq_net_fused_layers(const SesrqNet* net) {
+  return (net && net->fuse12 && chain2_supported(net->layers[1], net->layers[2])) ? 1 : 0;
+}
+
 size_t sesrq_ws_bytes(const SesrqNet* net, int B, int H, int W) {
   if (!net || B < 0 || H <= 0 || W <= 0) return 0;
   return plan_ws(net, B, H, W).total;
@@ -398,6 +409,7 @@ int sesrq_ws_read_act_i8(const SesrqNet* net, const void* d_ws, size_t ws_bytes,
   WsPlan p = plan_ws(net, B, H, W);
   if (ws_bytes < p.total) return SESRQ_ENOMEM;
   if (B > p.chunk) return SESRQ_EUNSUPPORTED;        // chunked forward reuses the buffers
+  if (domain == 2 && sesrq_net_fused_layers(net)) return SESRQ_EUNSUPPORTED;   // never materialised (sesrq_chain.cu)
   if (domain == 0 && !net->need_a0) return SESRQ_EUNSUPPORTED;   // fused into the layer-0 kernel
   const int C = (domain == 0) ? net->layers[0].c.cin : net->layers[domain - 1].c.cout;
   const uint8_t* act = static_cast<const uint8_t*>(d_ws) + p.off_a[domain];

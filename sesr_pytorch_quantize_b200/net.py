@@ -26,7 +26,7 @@ def _stream_ptr(device) -> C.c_void_p:
 class Int8Net:
     """Replaces GraphModule.forward of the sim.py graph (sim.py:82-114,205)."""
 
-    def __init__(self, cnet: CompiledNet, device=None, impl: int = _lib.IMPL_AUTO):
+    def __init__(self, cnet: CompiledNet, device=None, impl: int = _lib.IMPL_AUTO, fuse: Optional[bool] = None):
         self.lib = _lib.load_library()
         if not torch.cuda.is_available():
             raise _lib.SesrqError("sesrq needs a CUDA device (B200 / sm_100); no CPU fallback exists")
@@ -61,6 +61,8 @@ class Int8Net:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.sesrq_net_create(C.byref(d), C.byref(h)), "sesrq_net_create")
         self._h = h
+        if fuse is not None:            # None: the library default (on, unless SESRQ_FUSE=0)
+            self.set_fusion(fuse)
         self._ws: Optional[torch.Tensor] = None
         self._ws_shape = None
 
@@ -80,6 +82,19 @@ class Int8Net:
         impl, pe = C.c_int32(), C.c_int32()
         _lib.check(self.lib.sesrq_net_layer_info(self._h, layer, C.byref(impl), C.byref(pe)))
         return impl.value, pe.value
+
+    def set_fusion(self, enable: bool) -> bool:
+        """Layers 1 + 2 in one launch (csrc/sesrq_chain.cu; bit-identical results, domain 2 is then never written to HBM,
+        so read_activation(2) needs fusion off).  Returns the previous setting."""
+        prev = self.lib.sesrq_net_set_fusion(self._h, int(bool(enable)))
+        if prev < 0:
+            _lib.check(-prev, "sesrq_net_set_fusion")
+        return bool(prev)
+
+    @property
+    def fused(self) -> bool:
+        """True if the next forward runs layers 1 + 2 as one launch."""
+        return bool(self.lib.sesrq_net_fused_layers(self._h))
 
     def ws_bytes(self, B: int, H: int, W: int) -> int:
         return int(self.lib.sesrq_ws_bytes(self._h, B, H, W))

@@ -18,13 +18,17 @@ def sha(a):
 
 
 def build(g, impl):
+    """impl: a kernel family, or (family, fuse) -- fuse=False keeps layers 1 and 2 as separate launches (sesrq_net_set_fusion)."""
+    impl, fuse = impl if isinstance(impl, tuple) else (impl, None)
     cnet = compile_network([torch.from_numpy(w) for w in g.wf], [torch.from_numpy(b) for b in g.bf],
                            g.scales, g.zeros, g.r, pe_add_bits=g.pe_add_bit)
-    return Int8Net(cnet, impl=impl)
+    return Int8Net(cnet, impl=impl, fuse=fuse)
 
 
 def impl_ids():
-    return [pytest.param(IMPL_GENERIC, id="generic"), pytest.param(IMPL_AUTO, id="auto")]
+    # "auto" is the shipped default: tcgen05 kernels, layers 1 + 2 fused into one launch where the layouts allow it
+    return [pytest.param(IMPL_GENERIC, id="generic"), pytest.param(IMPL_AUTO, id="auto"),
+            pytest.param((IMPL_AUTO, False), id="auto_unfused")]
 
 
 @pytest.mark.parametrize("impl", impl_ids())
@@ -41,7 +45,10 @@ def test_golden_bit_exact(case, impl):
         try:
             q = net.read_activation(dom).cpu().numpy()
         except SesrqError:
-            continue    # fused away on this kernel family
+            # never written to HBM: the tcgen05 layer-0 kernel quantises the frame on the fly (domain 0), and layers
+            # 1 + 2 run as one launch when fusion is on (domain 2)
+            assert dom == 0 or (dom == 2 and net.fused), "domain %d should be readable" % dom
+            continue
         assert sha(q) == g.hashes["q%d" % dom], "q%d differs" % dom
 
 
