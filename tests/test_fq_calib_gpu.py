@@ -133,6 +133,9 @@ def test_kl_search_index_exact_vs_oracle():
         assert np.allclose(curve[fin], want[fin], rtol=1e-9, atol=1e-13)
 
 
+M16_EXCEPTIONS = {}          # case -> edges (0..4 = layers, 5 = residual) whose M16 is off by one; empty = 6 of 6 identical
+
+
 @pytest.mark.parametrize("case", ["x2_fixture", "x4_fixture", "nrdm_fixture"])
 def test_minmax_calibrator_reproduces_reference_thresholds(case):
     g = load_golden(case)
@@ -152,7 +155,12 @@ def test_minmax_calibrator_reproduces_reference_thresholds(case):
     want = list(zip([int(v) for v in g["M"]], [int(v) for v in g["n"]]))
     # (M16, n) come from truncation of s_i / s_j * s_w * 2^n: a last-ulp difference in a range can move M16 by one
     assert all(a[1] == b[1] and abs(a[0] - b[0]) <= 1 for a, b in zip(got, want))
-    print("identical (M16,n):", sum(a == b for a, b in zip(got, want)), "of 6")
+    differing = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
+    print("identical (M16,n) %s:" % case, 6 - len(differing), "of 6; differing edges", differing,
+          [(got[i], want[i]) for i in differing])
+    # the edges whose M16 differs by one from the reference's (observed ranges agree to rel 1e-5, not bit for bit: the
+    # reference's min/max come from an fp32 library conv, ours from the integer-exact one) -- pinned per case
+    assert differing == M16_EXCEPTIONS.get(case, []), "edges with a differing M16 changed: %s" % differing
 
 
 def test_kl_calibrator_two_pass_vs_oracle():
