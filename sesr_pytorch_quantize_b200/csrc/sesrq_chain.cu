@@ -379,7 +379,8 @@ conv_chain2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- one-time setup ----
+  // ---- one-time setup (overlaps the tail of the previous kernel of the stream: nothing here depends on it) ----
+  pdl_launch_dependents();
   for (uint32_t i = threadIdx.x; i < CH_W_BYTES / 16; i += blockDim.x) {
     reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(w_a) + i);
     reinterpret_cast<uint4*>(w_s + CH_WL_BYTES)[i] = __ldg(reinterpret_cast<const uint4*>(w_b) + i);
@@ -410,6 +411,7 @@ conv_chain2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
+  pdl_wait();                               // from here on the activations the previous kernel wrote are read
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -512,7 +514,8 @@ int launch_conv_chain2(const LayerDev& A, const LayerDev& Bl, const uint8_t* d_i
   static std::atomic<uint64_t> optin_done{0};
   if (int rc = ensure_smem_optin(conv_chain2_kernel, 227 * 1024, optin_done)) return rc;
   const int grid = std::min(G.num_strips, sms);
-  conv_chain2_kernel<<<grid, CH_THREADS, smem, st>>>(tmap, PA, PB, G, A.d_wumma, Bl.d_wumma, reinterpret_cast<uint4*>(d_out));
+  SESRQ_CUDA(launch_pdl(conv_chain2_kernel, grid, CH_THREADS, smem, st, tmap, PA, PB, G, (const uint8_t*)A.d_wumma, (const uint8_t*)Bl.d_wumma,
+                        reinterpret_cast<uint4*>(d_out)));
   SESRQ_LAUNCH_CHECK("conv_chain2_kernel");
   return SESRQ_OK;
 }

@@ -531,7 +531,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- one-time setup ----
+  // ---- one-time setup (overlaps the tail of the previous kernel of the stream: nothing here depends on it) ----
+  pdl_launch_dependents();
   for (uint32_t i = threadIdx.x; i < P.w_bytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(w_img) + i);
   fence_proxy_async();                      // weights were written through the generic proxy, UMMA reads via async proxy
@@ -555,6 +556,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
+  pdl_wait();                               // from here on the activations the previous kernel wrote are read
 
   const int tiles_per_frame = P.tiles_x * P.tiles_y;
 
@@ -678,6 +680,7 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();                               // the next layer may start its prologue now
   for (uint32_t i = threadIdx.x; i < P.w_bytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(w_img) + i);
   fence_proxy_async();
@@ -702,6 +705,7 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
+  pdl_wait();                               // from here on the activations the previous kernel wrote are read
   const int tiles_per_frame = P.tiles_x * P.tiles_y;
   const long long HW = (long long)P.H * P.W;
 
@@ -927,6 +931,11 @@ struct Tuning {
 #endif
   }
 };
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("SESRQ_PDL"); return !(e && atoi(e) == 0); }();
+  return on;
+}
+
 static const Tuning& tuning() {
   static const Tuning t;
   return t;
@@ -1103,8 +1112,8 @@ static int launch_one(const CUtensorMap& tmap, const UmmaParams& P, const LayerD
   auto kern = conv_umma_kernel<KS, NS, EPI, RS, COUT, OUTM, FLOOR, EPI_WARPS>;
   static std::atomic<uint64_t> optin_done{0};
   if (int rc = ensure_smem_optin(kern, 227 * 1024, optin_done)) return rc;
-  kern<<<grid, (CTRL_WARPS + EPI_WARPS) * 32, smem, st>>>(tmap, P, L.d_wumma, reinterpret_cast<const uint4*>(d_shortcut),
-                                                          reinterpret_cast<uint4*>(d_out), d_q5, d_y, fa, smap ? *smap : tmap);
+  SESRQ_CUDA(launch_pdl(kern, grid, (CTRL_WARPS + EPI_WARPS) * 32, smem, st, tmap, P, (const uint8_t*)L.d_wumma,
+                        reinterpret_cast<const uint4*>(d_shortcut), reinterpret_cast<uint4*>(d_out), d_q5, d_y, fa, smap ? *smap : tmap));
   SESRQ_LAUNCH_CHECK("conv_umma_kernel");
   return SESRQ_OK;
 }
@@ -1214,7 +1223,8 @@ static int launch_l0_one(const CUtensorMap& xmap, const UmmaParams& P, const Lay
   // the kernel also has ~4.2 KB of static shared memory; static + dynamic <= 227 KB
   static std::atomic<uint64_t> optin_done{0};
   if (int rc = ensure_smem_optin(kern, 227 * 1024 - 5 * 1024, optin_done)) return rc;
-  kern<<<grid, (CTRL_WARPS + EPI_WARPS + L0_BUILD_WARPS) * 32, smem, st>>>(xmap, P, L.d_wumma, d_x, reinterpret_cast<uint4*>(d_out));
+  SESRQ_CUDA(launch_pdl(kern, grid, (CTRL_WARPS + EPI_WARPS + L0_BUILD_WARPS) * 32, smem, st, xmap, P, (const uint8_t*)L.d_wumma, d_x,
+                        reinterpret_cast<uint4*>(d_out)));
   SESRQ_LAUNCH_CHECK("conv_umma_l0_kernel");
   return SESRQ_OK;
 }

@@ -61,6 +61,10 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// Programmatic dependent launch: the next kernel of the stream may start its prologue (weights to shared memory, barrier
+// init, TMEM allocation) while this one is still running; it must not touch memory the predecessor writes before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -562,6 +566,24 @@ void fill_epilogue_params(UmmaParams& P, const LayerConst& c, int ns);
 // (kernel instantiation, device).  cudaFuncSetAttribute is idempotent, so a race between two threads is benign.
 // `done`: one bit per device; the caller keeps one variable per kernel instantiation (a function-pointer type is shared
 // by all instantiations with the same signature, so it cannot live in here).
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait): every kernel launched this way calls
+// pdl_wait() before its first access to activations.  SESRQ_PDL=0 (read once) launches plainly.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <typename Kern>
 static int ensure_smem_optin(Kern kern, int bytes, std::atomic<uint64_t>& done) {
   int dev = 0;

@@ -100,6 +100,51 @@ class _Plan:
         self.kind, self.runner, self.version, self.info = kind, runner, version, info
 
 
+def _chain_topology_error(gm, modules, qf):
+    """The fused networks hard-wire ONE dataflow: conv i is fed by quantise(func_id i) -> PE split, its only
+    consumer is the PE adder with func_id i, and what the quantiser of layer i reads comes from layer i-1 alone -- plus
+    layer 0 at the residual add of the fake-quant graph (models/sesr.py:45; in the integer graph the shortcut travels
+    inside requan_conv2d_output, quan_func.py:546-567).  Counting node kinds is not enough: five convs wired differently
+    must be interpreted node by node.  Returns None if the wiring is the chain, else the reason."""
+    conv_nodes = [n for n in gm.graph.nodes if n.op == 'call_module' and type(modules[n.target]) is torch.nn.Conv2d]
+    owner = {}                                     # PE-adder node -> index of its conv
+    for i, cn in enumerate(conv_nodes):
+        split = cn.args[0] if cn.args else None
+        if not (isinstance(split, torch.fx.Node) and split.op == 'call_function' and split.target is qf.reshape_input_for_hardware_pe):
+            return 'conv %d is not fed by reshape_input_for_hardware_pe' % i
+        quant = split.args[0] if split.args else None
+        if not (isinstance(quant, torch.fx.Node) and quant.op == 'call_function' and quant.target is qf.quantize_asymmetrical_by_tensor
+                and quant.kwargs.get('func_id') == i):
+            return 'conv %d is not fed by the quantiser with func_id %d' % (i, i)
+        users = list(cn.users)
+        if len(users) != 1 or users[0].op != 'call_function' or users[0].target is not qf.PEs_and_bias_adder \
+                or users[0].kwargs.get('func_id') != i:
+            return 'conv %d does not feed PEs_and_bias_adder with func_id %d alone' % (i, i)
+        owner[users[0]] = i
+
+    def sources(node, seen):                       # conv indices (-1 = graph input) whose results reach `node`
+        if node in owner:
+            return {owner[node]}
+        if node.op == 'placeholder':
+            return {-1}
+        if node in seen:
+            return set()
+        seen.add(node)
+        out = set()
+        for a in node.all_input_nodes:
+            out |= sources(a, seen)
+        return out
+
+    has_add = any(n.op == 'call_function' and n.target in (operator.add, torch.add) for n in gm.graph.nodes)
+    for i, cn in enumerate(conv_nodes):
+        quant = cn.args[0].args[0]
+        src = sources(quant.args[0], set()) if quant.args and isinstance(quant.args[0], torch.fx.Node) else set()
+        want = {-1} if i == 0 else ({3, 0} if (i == 4 and has_add) else {i - 1})
+        if src != want:
+            return 'layer %d reads from %s, the chain needs %s' % (i, sorted(src), sorted(want))
+    return None
+
+
 def _analyse(gm):
     """Classify the graph: ('int8', info) / ('fq', info) / ('graph', reason)."""
     from myQL import quan_func as qf
@@ -125,6 +170,9 @@ def _analyse(gm):
                 adds += 1
     if len(convs) != 5 or len(splits) != 5 or len(merges) != 5 or len(shuffles) > 1:
         return 'graph', 'not the 5-conv chain'
+    why = _chain_topology_error(gm, modules, qf)
+    if why:
+        return 'graph', why
     modes = {k.get('exe_mode') for k in quants} | {k.get('exe_mode') for k in merges}
     if len(modes) != 1:
         return 'graph', 'mixed exe_mode'

@@ -105,6 +105,23 @@ def test_partial_graph_is_not_fused(fresh_state):
     assert gm.fusion_plan() == "graph"
 
 
+@pytest.mark.parametrize("qmode", [1, 0])
+def test_rewired_five_conv_graph_is_not_fused(qmode, fresh_state):
+    """Five convs with all the right node kinds but a different dataflow (layer 2 reads layer 0's output instead of
+    layer 1's) must not be executed as the hard-wired SESR chain: the analyser checks the wiring, not the node counts."""
+    from myQL import quan_func as qf
+    g = load_golden("x4_small")
+    gm = quantize_graph(collapsed_model(g, sim=(qmode == 1)), qmode)
+    assert gm.fusion_plan() == ("int8" if qmode == 1 else "fq")
+    quants = [n for n in gm.graph.nodes if n.op == "call_function" and n.target is qf.quantize_asymmetrical_by_tensor]
+    q1, q2 = quants[1], quants[2]
+    q2.args = (q1.args[0],) + tuple(q2.args[1:])          # layer 2 now consumes what layer 1 consumes
+    gm.graph.lint()
+    gm.recompile()
+    gm._sesrq_plan = None
+    assert gm.fusion_plan() == "graph"
+
+
 @pytest.mark.parametrize("case", SMALL_CASES)
 def test_weight_quantisation_equals_reference_dumps(case, fresh_state):
     import define as d
