@@ -138,32 +138,38 @@ __global__ void __launch_bounds__(256) fqb_quant_nchw_kernel(const float* __rest
 // NHWC16 fp32 -> operand bytes, 4 lanes per pixel: lane q reads the float4 of channels 4q .. 4q + 3 (consecutive lanes
 // read consecutive 16 B), quantises them, and a 4 x 4 byte transpose across the four lanes (two shuffles) leaves lane q
 // with word q of the pixel's uint4 -- PE-major byte order: word e, byte q  <->  channel 4q + e.
+constexpr int FQ_QUANT_UNROLL = 4;             // float4 per thread (independent loads in flight, frame constants amortised)
 __global__ void __launch_bounds__(256) fqb_quant_nhwc_kernel(const float4* __restrict__ x4, int HW,
                                                              const FqFrameParams* __restrict__ fp, uint32_t* __restrict__ act4) {
   const int f = blockIdx.y;                                                    // grid.y = frame: no per-thread division
-  const unsigned tf = blockIdx.x * blockDim.x + threadIdx.x;                   // one float4 each; whole warps stay together
-  const bool live = tf < (unsigned)HW * 4u;
+  const unsigned t0 = blockIdx.x * (blockDim.x * FQ_QUANT_UNROLL) + threadIdx.x;   // float4 index; whole warps stay together
+  const unsigned n4 = (unsigned)HW * 4u;
   const float4* x = x4 + (size_t)f * HW * 4;
   uint32_t* act = act4 + (size_t)f * HW * 4;
-  const unsigned t = tf;
-  uint32_t w = 0u;
-  if (live) {
-    const float zf = fp[f].in_z;
-    const ExactDiv div_s(fp[f].in_s);
-    const float4 v = __ldg(x + t);
-    const uint32_t b0 = (uint32_t)(quant_add_zero(div_s(v.x), zf) + 128);
-    const uint32_t b1 = (uint32_t)(quant_add_zero(div_s(v.y), zf) + 128);
-    const uint32_t b2 = (uint32_t)(quant_add_zero(div_s(v.z), zf) + 128);
-    const uint32_t b3 = (uint32_t)(quant_add_zero(div_s(v.w), zf) + 128);
-    w = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);                              // byte e = this lane's contribution to word e
+  const float zf = fp[f].in_z;
+  const ExactDiv div_s(fp[f].in_s);
+  float4 v[FQ_QUANT_UNROLL];
+#pragma unroll
+  for (int u = 0; u < FQ_QUANT_UNROLL; ++u) {
+    const unsigned t = t0 + u * blockDim.x;
+    v[u] = (t < n4) ? __ldg(x + t) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  // transpose: lane q ends with (lane0.byte q, lane1.byte q, lane2.byte q, lane3.byte q)
   const int q = threadIdx.x & 3;
-  uint32_t p1 = __shfl_xor_sync(0xffffffffu, w, 1);
-  w = (q & 1) ? __byte_perm(p1, w, 0x7351) : __byte_perm(w, p1, 0x6240);      // odd: (p.b1, own.b1, p.b3, own.b3); even: (own.b0, p.b0, own.b2, p.b2)
-  uint32_t p2 = __shfl_xor_sync(0xffffffffu, w, 2);
-  w = (q & 2) ? __byte_perm(p2, w, 0x7632) : __byte_perm(w, p2, 0x5410);      // upper pair: (p.h1, own.h1); lower pair: (own.h0, p.h0)
-  if (live) act[t] = w;
+#pragma unroll
+  for (int u = 0; u < FQ_QUANT_UNROLL; ++u) {
+    const unsigned t = t0 + u * blockDim.x;
+    const uint32_t b0 = (uint32_t)(quant_add_zero(div_s(v[u].x), zf) + 128);
+    const uint32_t b1 = (uint32_t)(quant_add_zero(div_s(v[u].y), zf) + 128);
+    const uint32_t b2 = (uint32_t)(quant_add_zero(div_s(v[u].z), zf) + 128);
+    const uint32_t b3 = (uint32_t)(quant_add_zero(div_s(v[u].w), zf) + 128);
+    uint32_t w = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);                     // byte e = this lane's contribution to word e
+    // transpose: lane q ends with (lane0.byte q, lane1.byte q, lane2.byte q, lane3.byte q)
+    uint32_t p1 = __shfl_xor_sync(0xffffffffu, w, 1);
+    w = (q & 1) ? __byte_perm(p1, w, 0x7351) : __byte_perm(w, p1, 0x6240);    // odd: (p.b1, own.b1, p.b3, own.b3); even: (own.b0, p.b0, own.b2, p.b2)
+    uint32_t p2 = __shfl_xor_sync(0xffffffffu, w, 2);
+    w = (q & 2) ? __byte_perm(p2, w, 0x7632) : __byte_perm(w, p2, 0x5410);    // upper pair: (p.h1, own.h1); lower pair: (own.h0, p.h0)
+    if (t < n4) act[t] = w;
+  }
 }
 
 // 2048-bin histogram of the first `nch` channels of an NHWC16 fp32 tensor over a fixed range (KL pass 2).  Per-CTA
@@ -450,7 +456,7 @@ int sesrq_fq_forward_batch(const SesrqFq* fq, const float* d_x, int B, int H, in
                                                    d_hist + (size_t)i * SESRQ_KL_BINS);
           SESRQ_LAUNCH_CHECK("fqb_hist_nhwc_kernel");
         }
-        fqb_quant_nhwc_kernel<<<dim3((unsigned)((HW * 4 + 255) / 256), (unsigned)nb), 256, 0, st>>>(
+        fqb_quant_nhwc_kernel<<<dim3((unsigned)((HW * 4 + 256 * FQ_QUANT_UNROLL - 1) / (256 * FQ_QUANT_UNROLL)), (unsigned)nb), 256, 0, st>>>(
             reinterpret_cast<const float4*>(in_t[i]), HW, fp, reinterpret_cast<uint32_t*>(act));
         SESRQ_LAUNCH_CHECK("fqb_quant_nhwc_kernel");
       }

@@ -637,7 +637,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 constexpr int L0_EP = 132;               // E row pitch in entries (X up to 127 + 4)
 constexpr int L0_SP = 136;               // S row pitch in words  (X + 3 up to 134)
-constexpr int L0_BUILD_WARPS = 8;
+#ifndef SESRQ_L0_BUILD_WARPS
+#define SESRQ_L0_BUILD_WARPS 8
+#endif
+#ifndef SESRQ_L0_EPI_WARPS
+#define SESRQ_L0_EPI_WARPS 12        // epilogue warps of the NS = 1 layer-0 kernel
+#endif
+constexpr int L0_BUILD_WARPS = SESRQ_L0_BUILD_WARPS;
+constexpr int L0_STATIC_SMEM = ((L0_BUILD_WARPS * (128 + 4) * 4 + 1023) / 1024) * 1024;   // stage_w (static shared memory), rounded up
 constexpr int L0_XP = 136;               // fp32 tile row pitch in floats = TMA box width: 132 pixels + up to 3 of alignment
                                          // (the box must start on a 16-byte boundary: an unaligned inner coordinate faults)
 constexpr int L0_XSTAGES = 4;            // fp32 tile buffers (upper bound; P.xstages are used)
@@ -1222,8 +1229,9 @@ static int launch_l0_one(const CUtensorMap& xmap, const UmmaParams& P, const Lay
   auto kern = conv_umma_l0_kernel<KS, NS, CIN, FLOOR, EPI_WARPS>;
   // the kernel also has ~4.2 KB of static shared memory; static + dynamic <= 227 KB
   static std::atomic<uint64_t> optin_done{0};
-  if (int rc = ensure_smem_optin(kern, 227 * 1024 - 5 * 1024, optin_done)) return rc;
-  SESRQ_CUDA(launch_pdl(kern, grid, (CTRL_WARPS + EPI_WARPS + L0_BUILD_WARPS) * 32, smem, st, xmap, P, (const uint8_t*)L.d_wumma, d_x,
+  if (int rc = ensure_smem_optin(kern, 227 * 1024 - L0_STATIC_SMEM, optin_done)) return rc;
+  // `smem` is the CTA's whole budget (the plan counts the static part in `fixed`): the dynamic request excludes it
+  SESRQ_CUDA(launch_pdl(kern, grid, (CTRL_WARPS + EPI_WARPS + L0_BUILD_WARPS) * 32, smem - L0_STATIC_SMEM, st, xmap, P, (const uint8_t*)L.d_wumma, d_x,
                         reinterpret_cast<uint4*>(d_out)));
   SESRQ_LAUNCH_CHECK("conv_umma_l0_kernel");
   return SESRQ_OK;
@@ -1239,7 +1247,7 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
   P.TW = cdiv(W, P.tiles_x);
   const uint32_t w_bytes = (uint32_t)2 * c.k * N * 16;
   // fixed part: weights, barriers, slack for alignment, and the kernel's 4 KB of static shared memory (stage_w)
-  const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (2 * MAX_STAGES + 2 * (TMEM_COLS / N) + 2 * L0_XSTAGES) + 64 + 1024 + 5 * 1024;
+  const size_t fixed = ((w_bytes + 127) & ~127u) + 8 * (2 * MAX_STAGES + 2 * (TMEM_COLS / N) + 2 * L0_XSTAGES) + 64 + 1024 + L0_STATIC_SMEM;
   const int sms = sm_count();
   // fp32 tiles by TMA need 16-byte aligned rows (W % 4 == 0), a 16-byte aligned base, and x = 0 -> pad code (z0 <= 127)
   EncodeTiledFn encode = get_encode_fn();
@@ -1305,11 +1313,11 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
 #define SESRQ_L0_NS(KS_, CIN_)                                                                              \
   do {                                                                                                      \
     if (needs_floor(c)) {                                                                                   \
-      if (ns == 1) return launch_l0_one<KS_, 1, CIN_, true, 12>(xmap, P, L, d_x, d_out, grid, smem, st);          \
+      if (ns == 1) return launch_l0_one<KS_, 1, CIN_, true, SESRQ_L0_EPI_WARPS>(xmap, P, L, d_x, d_out, grid, smem, st);          \
       if (ns == 2) return launch_l0_one<KS_, 2, CIN_, true, 16>(xmap, P, L, d_x, d_out, grid, smem, st);          \
       return launch_l0_one<KS_, 4, CIN_, true, 8>(xmap, P, L, d_x, d_out, grid, smem, st);                        \
     }                                                                                                       \
-    if (ns == 1) return launch_l0_one<KS_, 1, CIN_, false, 12>(xmap, P, L, d_x, d_out, grid, smem, st);           \
+    if (ns == 1) return launch_l0_one<KS_, 1, CIN_, false, SESRQ_L0_EPI_WARPS>(xmap, P, L, d_x, d_out, grid, smem, st);           \
     if (ns == 2) return launch_l0_one<KS_, 2, CIN_, false, 16>(xmap, P, L, d_x, d_out, grid, smem, st);           \
     return launch_l0_one<KS_, 4, CIN_, false, 8>(xmap, P, L, d_x, d_out, grid, smem, st);                         \
   } while (0)
