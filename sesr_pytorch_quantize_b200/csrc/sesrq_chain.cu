@@ -149,8 +149,8 @@ __device__ __forceinline__ void chain_wait3(const int lane, const bool need_src,
 
 // MMA issuer of one layer (one warp, one elected lane issues).  IS_A: source = input ring (one barrier pair per 16-row
 // block, filled by TMA), accumulator slots 0..15; else source = mid ring (one pair per 8-row group, filled by epilogue A),
-// slots 16..31.  INTERIOR blocks (all 16 source rows exist and each has its three output rows: every block of a strip but
-// the first and the last one or two) run a completely unrolled body: slot numbers, B offsets, N and the commit points are
+// slots 16..31.  FULL blocks (all 16 source rows exist and none lies beyond the last output row: every block of a strip but
+// the last one or two) run a completely unrolled body: slot numbers, B offsets, N and the commit points are
 // compile-time constants and no run-time test is left.  The few edge blocks take a rolled loop (the code must stay small:
 // the instruction cache, not the tensor pipe, limited the first version of this kernel -- profiles/r2_chain.txt).
 template <bool IS_A>
@@ -187,8 +187,9 @@ __device__ __forceinline__ void chain_issuer(const ChainGeom& G, const int lane,
       // barrier addresses of the two halves
       const uint32_t sfull0 = src_full_addr + (IS_A ? sslot : sslot * CH_HPB) * 8u;
       const uint32_t sempty0 = src_empty_addr + (IS_A ? sslot : sslot * CH_HPB) * 8u;
-      if (k >= 1 && r0 + CH_BLK - 1 <= n_out - 1) {
-        // ---------------- interior block ----------------
+      if (r0 + CH_BLK - 1 <= n_out - 1) {
+        // ---------------- full block (all 16 source rows exist, none is beyond the last output row) ----------------
+        const bool first = (k == 0);              // rows 0, 1 of a strip have no output rows -2, -1: three MMAs fewer
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           chain_wait3(lane, IS_A ? (h == 0) : true, sfull0 + (IS_A ? 0u : (uint32_t)h * 8u), spar, true, true,
@@ -205,15 +206,17 @@ __device__ __forceinline__ void chain_issuer(const ChainGeom& G, const int lane,
                 chain_mma_a(d_base, a_row1, w_units, idesc3, i - 1, 0);
                 chain_mma_c(d_base, a_pair, c_units, idesc4, i - 2, 0);
               } else {                                   // the slot ring wraps inside this pair (slots 14, 15, 0, 1)
-                chain_mma_a(d_base, a_row0, w_units, idesc2, 14, 0);
+                if (!first) {                            // output rows r0 - 2, r0 - 1 (the previous block's last two)
+                  chain_mma_a(d_base, a_row0, w_units, idesc2, 14, 0);
+                  chain_mma_a(d_base, a_row1, w_units, idesc1, 15, 0);
+                  chain_mma_c(d_base, a_pair, c_units, idesc2, 14, 0);
+                }
                 chain_mma_a(d_base, a_row0, w_units, idesc1, 0, 2);
-                chain_mma_a(d_base, a_row1, w_units, idesc1, 15, 0);
                 chain_mma_a(d_base, a_row1, w_units, idesc2, 0, 1);
-                chain_mma_c(d_base, a_pair, c_units, idesc2, 14, 0);
                 chain_mma_c(d_base, a_pair, c_units, idesc2, 0, 2);
               }
               // output row r + 1 - 2 = i - 1 closes a 4-row group when (i - 1) % 4 == 3: pairs i = 0, 4, 8, 12
-              if ((i & 3) == 0) umma_commit_addr(acc_full_addr + (uint32_t)(((i + 12) & 15) >> 2) * 8u);
+              if ((i & 3) == 0 && !(first && i == 0)) umma_commit_addr(acc_full_addr + (uint32_t)(((i + 12) & 15) >> 2) * 8u);
               if (IS_A) { if (i == 14) umma_commit_addr(sempty0); }
               else { if (pp == CH_HALF / 2 - 1) umma_commit_addr(sempty0 + (uint32_t)h * 8u); }
             }
