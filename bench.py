@@ -449,6 +449,20 @@ def main():
                  "minmax_threshold_hash": thr_hash, "minmax_zeros": [int(v) for v in mm_zeros],
                  "frame_set": "global: torch.rand seed 1234, %d frames, contiguous shards" % args.calib_frames,
                  "collectives": "all_reduce(MAX) over 12 floats; all_reduce(SUM) over int64 [6,2048]" if world > 1 else "none (1 rank)"}
+        # roofline of the min/max pass.  Algorithmic bytes: every activation of the fp32 fake-quant graph crosses HBM once
+        # per direction as fp32, 4 * (Cin + 4 * 16 + Cout) B/px (the reference's tensors; 316 B/px for SESR x2).  What the
+        # batched pass really moves: each hidden activation is written as fp32 by the conv epilogue (its per-frame range
+        # is only known when the whole frame is done), read back and written as operand bytes by the quantise pass, and
+        # read by the next conv: 4*Cin + 16 + 16 for layer 0, 64 + 64 + 16 + 16 per hidden layer, 64 + 64 + 4*Cout at the end
+        cal_px = (hi - lo) * ch * cw
+        alg_b = 4 * (cin + 4 * 16 + cout)
+        real_b = (4 * cin + 32) + 4 * 160 + (128 + 4 * cout)
+        mm_s = float(tc[0]) * 1e-3
+        calib["roofline"] = {"bound": "hbm", "what": "min/max calibration pass (fake-quant forward of all frames)",
+                             "alg_bytes_per_lr_px": alg_b, "moved_bytes_per_lr_px": real_b,
+                             "achieved": alg_b * cal_px / mm_s / 1e9, "moved_gbs": real_b * cal_px / mm_s / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": alg_b * cal_px / mm_s / 1e9 / peak,
+                             "frac_moved": real_b * cal_px / mm_s / 1e9 / peak}
         fq.close()
 
     # ---- the same step for the other output selections (y = what model(inps) returns; q5 = input.5.pt, SURVEY 8d's
