@@ -650,9 +650,15 @@ constexpr int L0_XP = 136;               // fp32 tile row pitch in floats = TMA 
 constexpr int L0_XSTAGES = 4;            // fp32 tile buffers (upper bound; P.xstages are used)
 
 // ExactDiv (sesrq_common.cuh) on two quotients per instruction (FMUL2 / FFMA2): lane-wise identical to the scalar sequence
+// max of three, NaN if any operand is NaN (max.NaN.f32, 3-input form of sm_100)
+__device__ __forceinline__ float max3_nan(float a, float b, float c) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// The operands must already lie in [-lim, lim] (ExactDiv's range clamp): the row builder checks a whole row's worth of
+// values with a handful of 3-input maxima and clamps only in the (never seen in image data) case that one is outside.
 __device__ __forceinline__ float2 exact_div2(const ExactDiv& d, float2 x) {
-  x.x = fminf(fmaxf(x.x, -d.lim), d.lim);
-  x.y = fminf(fmaxf(x.y, -d.lim), d.lim);
   const float2 q0 = f2_mul(x, d.rcp);
   const float2 e = f2_fma3(make_float2(-d.s, -d.s), q0, x);
   return f2_fma3(make_float2(d.rcp, d.rcp), e, q0);
@@ -808,6 +814,22 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
           for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int c = 0; c < CIN; ++c) v[u][c] = xr[c * rp * L0_XP + 32 * u];
+          {
+            // ExactDiv's operand range [-lim, lim] (lim / s = 2^40: beyond it the code saturates): test all of the
+            // lane's values at once; !(m <= lim) also catches NaN.  The clamp itself runs only if some lane needs it.
+            float m = 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; u += 2)
+#pragma unroll
+              for (int c = 0; c < CIN; ++c) m = max3_nan(m, fabsf(v[u][c]), fabsf(v[u + 1][c]));
+            const bool wild = !(m <= div_s0.lim);
+            if (__any_sync(0xffffffffu, wild)) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) v[u][c] = fminf(fmaxf(v[u][c], -div_s0.lim), div_s0.lim);
+            }
+          }
           uint32_t w0[4];
 #pragma unroll
           for (int u = 0; u < 4; u += 2) {
