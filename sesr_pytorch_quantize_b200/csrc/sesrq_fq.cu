@@ -155,13 +155,25 @@ __global__ void __launch_bounds__(256) fqb_quant_nhwc_kernel(const float4* __res
     v[u] = (t < n4) ? __ldg(x + t) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const int q = threadIdx.x & 3;
+  // ExactDiv's operand range: tested once per float4 (activations of a real frame are always inside); a value outside
+  // or NaN sends the whole warp through the clamps
+  bool ok = true;
+#pragma unroll
+  for (int u = 0; u < FQ_QUANT_UNROLL; ++u) ok = ok && div_s.in_range4(v[u]);
+  if (__any_sync(0xffffffffu, !ok)) {
+#pragma unroll
+    for (int u = 0; u < FQ_QUANT_UNROLL; ++u) {
+      v[u].x = fminf(fmaxf(v[u].x, -div_s.lim), div_s.lim); v[u].y = fminf(fmaxf(v[u].y, -div_s.lim), div_s.lim);
+      v[u].z = fminf(fmaxf(v[u].z, -div_s.lim), div_s.lim); v[u].w = fminf(fmaxf(v[u].w, -div_s.lim), div_s.lim);
+    }
+  }
 #pragma unroll
   for (int u = 0; u < FQ_QUANT_UNROLL; ++u) {
     const unsigned t = t0 + u * blockDim.x;
-    const uint32_t b0 = (uint32_t)(quant_add_zero(div_s(v[u].x), zf) + 128);
-    const uint32_t b1 = (uint32_t)(quant_add_zero(div_s(v[u].y), zf) + 128);
-    const uint32_t b2 = (uint32_t)(quant_add_zero(div_s(v[u].z), zf) + 128);
-    const uint32_t b3 = (uint32_t)(quant_add_zero(div_s(v[u].w), zf) + 128);
+    const uint32_t b0 = (uint32_t)(quant_add_zero(div_s.unclamped(v[u].x), zf) + 128);
+    const uint32_t b1 = (uint32_t)(quant_add_zero(div_s.unclamped(v[u].y), zf) + 128);
+    const uint32_t b2 = (uint32_t)(quant_add_zero(div_s.unclamped(v[u].z), zf) + 128);
+    const uint32_t b3 = (uint32_t)(quant_add_zero(div_s.unclamped(v[u].w), zf) + 128);
     uint32_t w = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);                     // byte e = this lane's contribution to word e
     // transpose: lane q ends with (lane0.byte q, lane1.byte q, lane2.byte q, lane3.byte q)
     uint32_t p1 = __shfl_xor_sync(0xffffffffu, w, 1);

@@ -807,8 +807,10 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         __syncwarp();
         const float* xsrc = reinterpret_cast<const float*>(region2 + (size_t)xs * P.xstage_bytes) + delta + lane;
         uint4* e = reinterpret_cast<uint4*>(e0 + (size_t)st * P.stage_bytes) + lane;
-        for (int row = bwid; row < rows; row += L0_BUILD_WARPS) {
-          const float* xr = xsrc + row * L0_XP;
+        // row pointers advance by constants (the compiler re-derived them from `row` with ~10 IMADs per row)
+        const float* xr = xsrc + bwid * L0_XP;
+        uint4* er = e + bwid * L0_EP;
+        for (int row = bwid; row < rows; row += L0_BUILD_WARPS, xr += L0_BUILD_WARPS * L0_XP, er += L0_BUILD_WARPS * L0_EP) {
           float v[4][CIN];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
@@ -846,7 +848,6 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 #pragma unroll
           for (int u = 0; u < 4; ++u) sw[32 * u + lane] = w0[u];
           __syncwarp();
-          uint4* er = e + row * L0_EP;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const uint32_t* s1 = sw + 32 * u + lane + 1;
