@@ -43,7 +43,12 @@ constexpr uint32_t CH_ROW_BYTES = UMMA_M * 16;          // one 128-pixel row of 
 constexpr uint32_t CH_BLK_BYTES = CH_BLK * CH_ROW_BYTES;
 constexpr int CH_EPI_WARPS = 8;                         // per layer: two warpgroups, each takes 2 rows of every 4-row group
 constexpr int CH_WROWS = CH_RG / (CH_EPI_WARPS / 4);    // rows of a group per warpgroup
-constexpr int CH_THREADS = (4 + 2 * CH_EPI_WARPS) * 32;
+#ifndef SESRQ_CHAIN_BANDS
+#define SESRQ_CHAIN_BANDS 0          // 1: two issuing threads per layer (bands of 8 rows; measured slower: +11 % MMAs), 0: one per layer
+#endif
+constexpr bool CH_BANDS = SESRQ_CHAIN_BANDS != 0;
+constexpr int CH_CTRL_WARPS = CH_BANDS ? 8 : 4;          // warp 0 TMA; bands: warps 1 / 3 layer-A issuers, 2 / 4 layer-B issuers; else warps 1, 2
+constexpr int CH_THREADS = (CH_CTRL_WARPS + 2 * CH_EPI_WARPS) * 32;
 constexpr int CH_NCOLS = 16;                            // accumulator columns per row slot (NS = 1)
 constexpr int CH_NTOT = 3 * CH_NCOLS;                   // B image rows per K half (3 vertical taps)
 constexpr uint32_t CH_W_BYTES = 2 * 2 * CH_NTOT * 16;   // 2 tap pairs x 2 K halves
@@ -268,6 +273,161 @@ __device__ __forceinline__ void chain_issuer(const ChainGeom& G, const int lane,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Band-parallel issue: TWO issuing threads per layer.  A band = 8 output rows = one half of the 16-slot accumulator ring;
+// thread t of a layer takes the bands j == t (mod 2), so it only ever touches the slots 8t .. 8t+7 and the accumulator
+// groups 2t, 2t+1 -- the two threads never accumulate into the same slot and each commits its own groups.  A band reads
+// the 10 source rows 8j .. 8j+9 (its two edge rows are read again by the next band: 15 MMAs per 8 rows instead of 13.5,
+// but two threads issue them).  Source buffers are therefore released by several readers:
+//   input block k (16 rows)  <- bands 2k-1 (rows 0, 1), 2k, 2k+1          in_empty count 3
+//   mid half h (8 rows)      <- bands h-1 (rows 0, 1), h                   mid_empty count 2
+// where the band -1 of a strip does not exist: thread 1 (the owner of odd bands) arrives in its place at strip start.
+// Bands past the last output row are phantoms: the same waits and arrivals, no MMAs.
+// ------------------------------------------------------------------------------------------------
+// per-row scheme (two tap-pair MMAs) clipped to the band's output rows [o_min, o_max]
+__device__ __forceinline__ void chain_issue_row_clipped(const int r, const int o_min, const int o_max, const uint32_t d_base,
+                                                        const uint32_t a_row_lo, const uint32_t w_units, const uint32_t idesc0) {
+  const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t b_lbo = (uint32_t)CH_NTOT << 16;
+  const int o_first = r - 2;
+  const int o_lo = max(o_first, o_min);
+  const int o_hi = min(r, o_max);
+  if (o_lo > o_hi) return;
+  const int cnt = o_hi - o_lo + 1;                       // a band never wraps around the ring
+  const int jblk = o_lo - o_first;
+  const uint32_t idesc = idesc0 | ((uint32_t)((cnt * CH_NCOLS) >> 3) << 17);
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+    umma_i8(d_base + (uint32_t)((o_lo & (CH_BLK - 1)) * CH_NCOLS), make_desc(a_row_lo + (uint32_t)(q * 2), desc_hi),
+            make_desc((w_units + (uint32_t)(q * 2 * CH_NTOT + jblk * CH_NCOLS)) | b_lbo, desc_hi), idesc, 1u);
+}
+
+// lanes 0..3 poll up to four barriers with one instruction: two source barriers, two accumulator groups
+__device__ __forceinline__ void chain_wait4(const int lane, const bool n0, const uint32_t b0, const uint32_t p0, const bool n1,
+                                            const uint32_t b1, const uint32_t p1, const bool n2, const bool n3,
+                                            const uint32_t bacc, const uint32_t pacc) {
+  const bool mine = (lane == 0 && n0) || (lane == 1 && n1) || (lane == 2 && n2) || (lane == 3 && n3);
+  const uint32_t bar = lane == 0 ? b0 : (lane == 1 ? b1 : bacc + (lane == 3 ? 8u : 0u));
+  const uint32_t par = lane == 0 ? p0 : (lane == 1 ? p1 : pacc);
+  uint32_t ok;
+  do {
+    ok = 1u;
+    if (mine)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(ok) : "r"(bar), "r"(par), "r"(MBAR_SUSPEND_NS) : "memory");
+  } while (!__all_sync(0xffffffffu, ok != 0u));
+  tc_fence_after();
+}
+
+template <bool IS_A>
+__device__ __forceinline__ void chain_band_issuer(const ChainGeom& G, const int t, const int lane, const uint32_t tmem_base,
+                                                  const uint8_t* w_s, const uint8_t* src_ring, uint64_t* const src_full,
+                                                  uint64_t* const src_empty, uint64_t* const acc_full, uint64_t* const acc_empty) {
+  constexpr uint32_t SRC_BLOCKS = IS_A ? CH_IN_BLOCKS : CH_MID_BLOCKS;
+  const uint32_t w_units = (smem_u32(w_s) & 0x3FFFFu) >> 4;
+  const uint32_t c_units = w_units + (CH_W_BYTES >> 4);
+  const uint32_t src_units = (smem_u32(src_ring) & 0x3FFFFu) >> 4;
+  const uint32_t d_base = tmem_base + (IS_A ? 0u : (uint32_t)(CH_BLK * CH_NCOLS));
+  const uint32_t idesc0 = G.idesc;
+  const uint32_t idesc1 = idesc0 | ((uint32_t)((1 * CH_NCOLS) >> 3) << 17);
+  const uint32_t idesc2 = idesc0 | ((uint32_t)((2 * CH_NCOLS) >> 3) << 17);
+  const uint32_t idesc3 = idesc0 | ((uint32_t)((3 * CH_NCOLS) >> 3) << 17);
+  const uint32_t idesc4 = idesc0 | ((uint32_t)((4 * CH_NCOLS) >> 3) << 17);
+  const uint32_t acc_full_addr = smem_u32(acc_full) + (uint32_t)(2 * t) * 8u;      // this thread's two groups
+  const uint32_t acc_empty_addr = smem_u32(acc_empty) + (uint32_t)(2 * t) * 8u;
+  const uint32_t src_full_addr = smem_u32(src_full), src_empty_addr = smem_u32(src_empty);
+  const int S0 = 8 * t;                                  // first accumulator slot of this thread's bands
+  uint32_t sb = 0;                                       // running source block counter (input blocks / mid blocks)
+  uint32_t ob = 0;                                       // running output block counter of this layer
+  for (int s = blockIdx.x; s < G.num_strips; s += gridDim.x) {
+    const ChainStrip st = chain_strip(G, s);
+    const int n_src = IS_A ? st.sh + 4 : st.sh + 2;
+    const int n_out = n_src - 2;
+    const int nb_src = (n_src + CH_BLK - 1) / CH_BLK;
+    const int nb_out = (n_out + CH_BLK - 1) / CH_BLK;
+    // source barrier of (block k, half h): layer A has one pair per block, layer B one per 8-row half
+    auto sidx = [&](uint32_t blk, int h) { return IS_A ? (blk % SRC_BLOCKS) : (blk % SRC_BLOCKS) * CH_HPB + (uint32_t)h; };
+    auto spar = [&](uint32_t blk) { return (blk / SRC_BLOCKS) & 1u; };
+    if (t == 1) {
+      // the strip's first source buffer has no "previous band": arrive in its place, once its data has landed (so that
+      // the arrival counts for this use of the buffer, not for the previous one)
+      mbar_wait(&src_full[sidx(sb, 0)], spar(sb));
+      if (lane == 0) mbar_arrive(&src_empty[sidx(sb, 0)]);
+      __syncwarp();
+    }
+    for (int j = t; j < 2 * nb_src; j += 2) {
+      const int k = j >> 1;                              // source block of the band's first 8 rows (half t of it)
+      const uint32_t blk = sb + (uint32_t)k;
+      const bool has_acc = k < nb_out;                   // the band's accumulator groups exist (real or phantom)
+      const bool real = 8 * j < n_out;
+      // second source buffer: the band's rows 8, 9.  Layer A: the next block (odd bands only); layer B: the next half.
+      const bool two = IS_A ? (t == 1 && k + 1 < nb_src) : (j + 1 < 2 * nb_src);
+      const uint32_t blk2 = (IS_A || t == 1) ? blk + 1 : blk;
+      const uint32_t i0 = sidx(blk, t), i1 = sidx(blk2, IS_A ? 0 : 1 - t);
+      chain_wait4(lane, true, src_full_addr + i0 * 8u, spar(blk), two, src_full_addr + i1 * 8u, spar(blk2), has_acc, has_acc,
+                  acc_empty_addr, (ob + (uint32_t)k) & 1u);
+      if (elect_one()) {
+        const uint32_t a_lo = (src_units + (blk % SRC_BLOCKS) * (CH_BLK * UMMA_M) + (uint32_t)(S0 * UMMA_M)) | (1u << 16);   // row 8j
+        const uint32_t a_hi = (t == 0) ? a_lo + 8u * UMMA_M                                                              // rows 8j+8, 8j+9
+                                       : ((src_units + (blk2 % SRC_BLOCKS) * (CH_BLK * UMMA_M)) | (1u << 16));
+        if (real) {
+          if (8 * j + 7 <= n_out - 1) {
+            // ---------- full band: 15 MMAs, everything a compile-time offset from the two row bases ----------
+#pragma unroll
+            for (int pp = 0; pp < 5; ++pp) {
+              const uint32_t a0 = pp < 4 ? a_lo + (uint32_t)(2 * pp * UMMA_M) : a_hi;
+              const uint32_t a1 = a0 + (uint32_t)UMMA_M;
+              const uint32_t ap = (a0 & 0xFFFFu) | ((uint32_t)UMMA_M << 16);
+              if (pp == 0) {                             // rows 0, 1: output rows 0, 1 of the band only
+                chain_mma_a(d_base, a0, w_units, idesc1, S0, 2);
+                chain_mma_a(d_base, a1, w_units, idesc2, S0, 1);
+                chain_mma_c(d_base, ap, c_units, idesc2, S0, 2);
+              } else if (pp < 4) {                       // rows 2p, 2p+1: output rows 2p-2 .. 2p+1
+                chain_mma_a(d_base, a0, w_units, idesc3, S0 + 2 * pp - 2, 0);
+                chain_mma_a(d_base, a1, w_units, idesc3, S0 + 2 * pp - 1, 0);
+                chain_mma_c(d_base, ap, c_units, idesc4, S0 + 2 * pp - 2, 0);
+              } else {                                   // rows 8, 9: output rows 6, 7 of the band only
+                chain_mma_a(d_base, a0, w_units, idesc2, S0 + 6, 0);
+                chain_mma_a(d_base, a1, w_units, idesc1, S0 + 7, 0);
+                chain_mma_c(d_base, ap, c_units, idesc2, S0 + 6, 0);
+              }
+              if (pp == 2) umma_commit_addr(acc_full_addr);              // output rows 0..3 are complete after source row 5
+              if (pp == 4) umma_commit_addr(acc_full_addr + 8u);         // rows 4..7 after source row 9
+            }
+          } else {
+            // ---------- last band of a strip with fewer than 8 output rows: rolled, per-row scheme ----------
+            const int o_min = 8 * j, o_max = n_out - 1;
+#pragma unroll 1
+            for (int i = 0; i < 10; ++i) {
+              const int r = 8 * j + i;
+              if (r >= n_src) break;
+              const uint32_t a_row = i < 8 ? a_lo + (uint32_t)(i * UMMA_M) : a_hi + (uint32_t)((i - 8) * UMMA_M);
+              chain_issue_row_clipped(r, o_min, o_max, d_base, a_row, w_units, idesc0);
+              const int o = r - 2;
+              if (o >= o_min && ((o & 3) == 3 || o == o_max)) umma_commit_addr(acc_full_addr + (uint32_t)((o >> 2) & 1) * 8u);
+            }
+            // a group of this band that has no output row at all is a phantom
+            if (8 * j + 4 >= n_out) mbar_arrive(&acc_full[2 * t + 1]);
+          }
+          umma_commit_addr(src_empty_addr + i0 * 8u);    // both source buffers: released when this band's MMAs have retired
+          if (two) umma_commit_addr(src_empty_addr + i1 * 8u);
+        } else {
+          // ---------- phantom band ----------
+          if (has_acc) { mbar_arrive(&acc_full[2 * t]); mbar_arrive(&acc_full[2 * t + 1]); }
+          mbar_arrive(&src_empty[i0]);
+          if (two) mbar_arrive(&src_empty[i1]);
+        }
+      }
+      __syncwarp();
+    }
+    sb += (uint32_t)nb_src;
+    ob += (uint32_t)nb_out;
+  }
+}
+
 // Epilogue warps of one layer (8 warps = two warpgroups taking alternate groups of 4 rows).
 //   IS_A: codes -> mid ring (shared memory), out-of-frame positions forced to the pad byte;  else: codes -> global memory.
 template <bool IS_A>
@@ -322,26 +482,32 @@ __device__ __forceinline__ void chain_epilogue(const UmmaParams& P, const ChainG
         if (o0 < n_out) {
           const uint32_t taddr0 = tq + (uint32_t)(row0 * CH_NCOLS);
           uint4* const mrow = reinterpret_cast<uint4*>(mid_ring + (size_t)mslot * CH_BLK_BYTES) + row0 * UMMA_M + ox;
+          // both rows of this warpgroup's share at once: one wait for the two TMEM loads, then two independent
+          // conversion chains in one basic block (the warps are latency-bound: twice the ILP per warp)
+          static_assert(CH_WROWS == 2, "two rows per warpgroup and group");
           int acc[2][1][16];
           slot_load<1>(taddr0, acc[0]);
+          slot_load<1>(taddr0 + (uint32_t)CH_NCOLS, acc[1]);
+          tmem_ld_wait();
+          slot_fence<1>(acc[0]);
+          slot_fence<1>(acc[1]);
+          slot_store<1>(taddr0, cinit);
+          slot_store<1>(taddr0 + (uint32_t)CH_NCOLS, cinit);
+          uint4 code[2];
 #pragma unroll
-          for (int i = 0; i < CH_WROWS; ++i) {
-            const int cur = i & 1;
-            tmem_ld_wait();
-            slot_fence<1>(acc[cur]);
-            if (i + 1 < CH_WROWS) slot_load<1>(taddr0 + (uint32_t)((i + 1) * CH_NCOLS), acc[(i + 1) & 1]);
-            slot_store<1>(taddr0 + (uint32_t)(i * CH_NCOLS), cinit);
-            uint4 code;
-            epilogue_pixel<1, EPI_PLAIN, 1, 0, 0, false>(P, acc[cur], make_uint4(0u, 0u, 0u, 0u), &code, nullptr, nullptr, 0,
+          for (int i = 0; i < 2; ++i)
+            epilogue_pixel<1, EPI_PLAIN, 1, 0, 0, false>(P, acc[i], make_uint4(0u, 0u, 0u, 0u), &code[i], nullptr, nullptr, 0,
                                                          relu_floor, true);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
             const int o = o0 + i;
             const int fy = fy0 + o;
             if (IS_A) {
               // out-of-frame positions are the next layer's zero padding: byte 0 = code -128 (its z_in <= -128)
               const bool in_frame = col_ok && fy >= 0 && fy < G.H;
-              mrow[i * UMMA_M] = in_frame ? code : make_uint4(0u, 0u, 0u, 0u);
+              mrow[i * UMMA_M] = in_frame ? code[i] : make_uint4(0u, 0u, 0u, 0u);
             } else {
-              if (col_ok && o < n_out) orow0[(long long)o * G.W] = code;
+              if (col_ok && o < n_out) orow0[(long long)o * G.W] = code[i];
             }
           }
         }
@@ -401,12 +567,12 @@ conv_chain2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
-    for (int i = 0; i < CH_IN_BLOCKS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
+    for (int i = 0; i < CH_IN_BLOCKS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], CH_BANDS ? 3 : 1); }
     for (int i = 0; i < CH_GPB; ++i) {
       mbar_init(&acc_full_a[i], 1); mbar_init(&acc_empty_a[i], CH_EPI_WARPS);
       mbar_init(&acc_full_b[i], 1); mbar_init(&acc_empty_b[i], CH_EPI_WARPS);
     }
-    for (int i = 0; i < CH_MID_BLOCKS * CH_HPB; ++i) { mbar_init(&mid_full[i], 2 * CH_EPI_WARPS); mbar_init(&mid_empty[i], 1); }
+    for (int i = 0; i < CH_MID_BLOCKS * CH_HPB; ++i) { mbar_init(&mid_full[i], 2 * CH_EPI_WARPS); mbar_init(&mid_empty[i], CH_BANDS ? 2 : 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_base_s, TMEM_COLS);
@@ -431,13 +597,17 @@ conv_chain2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (CH_BANDS && (warp == 1 || warp == 3)) {
+    chain_band_issuer<true>(G, warp >> 1, lane, tmem_base, w_s, in_ring, in_full, in_empty, acc_full_a, acc_empty_a);
+  } else if (CH_BANDS && (warp == 2 || warp == 4)) {
+    chain_band_issuer<false>(G, (warp >> 1) - 1, lane, tmem_base, w_s + CH_WL_BYTES, mid_ring, mid_full, mid_empty, acc_full_b, acc_empty_b);
+  } else if (!CH_BANDS && warp == 1) {
     chain_issuer<true>(G, lane, tmem_base, w_s, in_ring, in_full, in_empty, acc_full_a, acc_empty_a);
-  } else if (warp == 2) {
+  } else if (!CH_BANDS && warp == 2) {
     chain_issuer<false>(G, lane, tmem_base, w_s + CH_WL_BYTES, mid_ring, mid_full, mid_empty, acc_full_b, acc_empty_b);
-  } else if (warp >= 4) {
+  } else if (warp >= CH_CTRL_WARPS) {
     // ================= epilogues: warps 4-11 layer A (-> mid ring), warps 12-19 layer B (-> global memory) =================
-    const int ew = warp - 4;
+    const int ew = warp - CH_CTRL_WARPS;
     if (ew < CH_EPI_WARPS) chain_epilogue<true>(PA, G, ew, lane, tmem_base, acc_full_a, acc_empty_a, mid_full, mid_empty, mid_ring, out);
     else chain_epilogue<false>(PB, G, ew, lane, tmem_base, acc_full_b, acc_empty_b, mid_full, mid_empty, mid_ring, out);
   }
