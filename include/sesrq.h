@@ -99,6 +99,17 @@ void sesrq_net_destroy(SesrqNet* net);
  * weight-norm bound proved the PE clamps inert for it */
 int sesrq_net_layer_info(const SesrqNet* net, int layer, int32_t* impl, int32_t* pe_exact);
 
+/* Accumulator layout the tcgen05 path chose for a layer (csrc/sesrq_umma.cu header): how the reference's per-PE 18-bit
+ * clamp (quan_func.py:338-370) is honoured.  NS1: provably inert, one 16-column set; SPARE: the few (channel, PE) sums that
+ * can clamp ride in the unused columns 12..15 of a <= 12-channel final layer; NS2: in a second set of 4 correction
+ * columns; NS4: four PE-masked sets and the literal clamp tree.  0 = the layer runs on the generic dp4a path. */
+#define SESRQ_LAYOUT_GENERIC 0
+#define SESRQ_LAYOUT_NS1 1
+#define SESRQ_LAYOUT_SPARE 2
+#define SESRQ_LAYOUT_NS2 3
+#define SESRQ_LAYOUT_NS4 4
+int sesrq_net_layer_layout(const SesrqNet* net, int layer);   /* SESRQ_LAYOUT_* or a negative error code */
+
 /* Layer fusion.  When residual_block.0 and residual_block.1 (layers 1, 2: plain 3x3, 16 -> 16 channels, no PE clamp that
  * can fire) both run on the tcgen05 path, sesrq_net_forward_i8 executes them in ONE launch and hands the intermediate
  * codes (the reference's input.2.pt) from the first to the second through shared memory -- they never reach HBM

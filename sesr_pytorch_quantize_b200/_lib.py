@@ -74,6 +74,7 @@ SIGNATURES = {
     "sesrq_net_forward_i8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "sesrq_net_forward_i8_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "sesrq_net_profile_enable": (_i, [_vp, _i]),
+    "sesrq_net_layer_layout": (_i, [_vp, _i]),
     "sesrq_net_set_fusion": (_i, [_vp, _i]),
     "sesrq_net_fused_layers": (_i, [_vp]),
     "sesrq_net_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -315,6 +315,11 @@ int sesrq_net_fused_layers(const SesrqNet* net) {
   return (net && net->fuse12 && chain2_supported(net->layers[1], net->layers[2])) ? 1 : 0;
 }
 
+int sesrq_net_layer_layout(const SesrqNet* net, int layer) {
+  if (!net || layer < 0 || layer >= SESRQ_NUM_LAYERS) return SESRQ_EINVAL;
+  return net->layers[layer].impl == SESRQ_IMPL_UMMA ? net->layers[layer].layout : SESRQ_LAYOUT_GENERIC;
+}
+
 size_t sesrq_ws_bytes(const SesrqNet* net, int B, int H, int W) {
   if (!net || B < 0 || H <= 0 || W <= 0) return 0;
   return plan_ws(net, B, H, W).total;

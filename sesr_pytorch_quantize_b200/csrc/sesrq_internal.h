@@ -36,6 +36,7 @@ struct LayerDev {
   uint8_t* d_wumma = nullptr;    // tcgen05 path: B operand image (see sesrq_umma.cu)
   int impl = SESRQ_IMPL_GENERIC;
   int umma_n = 16;               // accumulator columns per 128-pixel block (16 fast / 64 pe-exact)
+  int layout = 0;                // SESRQ_LAYOUT_*: which accumulator layout the tcgen05 path chose (0 = generic path)
 };
 
 // ---- generic (CUDA-core) path: sesrq_generic.cu -------------------------------------------------

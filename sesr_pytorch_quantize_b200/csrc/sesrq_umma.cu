@@ -1083,6 +1083,7 @@ static int umma_prepare_layer0(LayerDev& L, const int8_t* w) {
   const int ns = accumulator_sets(c);
   const int N = 16 * ns, NTOT = c.k * N;
   L.umma_n = N;
+  L.layout = ns == 4 ? SESRQ_LAYOUT_NS4 : (ns == 2 ? SESRQ_LAYOUT_NS2 : (spare_column_layout(c) ? SESRQ_LAYOUT_SPARE : SESRQ_LAYOUT_NS1));
   std::vector<uint8_t> img((size_t)2 * NTOT * 16, 0);
   for (int h = 0; h < 2; ++h)
     for (int jblk = 0; jblk < c.k; ++jblk) {
@@ -1110,6 +1111,7 @@ int umma_prepare_layer(LayerDev& L, const int8_t* w) {
   const int ns = accumulator_sets(c);
   const int N = 16 * ns, NTOT = c.k * N;
   L.umma_n = N;
+  L.layout = ns == 4 ? SESRQ_LAYOUT_NS4 : (ns == 2 ? SESRQ_LAYOUT_NS2 : (spare_column_layout(c) ? SESRQ_LAYOUT_SPARE : SESRQ_LAYOUT_NS1));
   std::vector<uint8_t> img((size_t)pairs * 2 * NTOT * 16, 0);
   const bool natural = (c.epi == EPI_FINAL);
   for (int q = 0; q < pairs; ++q)

@@ -83,6 +83,13 @@ class Int8Net:
         _lib.check(self.lib.sesrq_net_layer_info(self._h, layer, C.byref(impl), C.byref(pe)))
         return impl.value, pe.value
 
+    def layer_layout(self, layer: int) -> str:
+        """Accumulator layout of a layer on the tcgen05 path: 'ns1' / 'spare' / 'ns2' / 'ns4', or 'generic' (dp4a path)."""
+        v = self.lib.sesrq_net_layer_layout(self._h, layer)
+        if v < 0:
+            _lib.check(v, "sesrq_net_layer_layout")
+        return ("generic", "ns1", "spare", "ns2", "ns4")[v]
+
     def set_fusion(self, enable: bool) -> bool:
         """Layers 1 + 2 in one launch (csrc/sesrq_chain.cu; bit-identical results, domain 2 is then never written to HBM,
         so read_activation(2) needs fusion off).  Returns the previous setting."""

@@ -70,3 +70,28 @@ def test_generator_reaches_every_layout():
     impls = {s[0] for s in seen}
     assert 1 in impls and 2 in impls                      # generic and tcgen05 both exercised
     assert (2, 0) in seen and (2, 1) in seen              # tcgen05 with inert clamps and with clamps that can fire
+
+
+def test_every_accumulator_layout_is_reached_and_bit_exact():
+    """NS = 1, the spare-column layout, NS = 2 and NS = 4 (csrc/sesrq_umma.cu header) must EACH be selected by some network
+    of the test set -- the random networks above plus the reference fixtures -- so that the bit-exactness tests cover all
+    four epilogue / weight-image variants, not only the common one."""
+    from conftest import load_golden, ALL_CASES
+    layouts = {}
+    for seed in range(24):
+        wf, bf, scales, zeros, r, pe_add_bit = random_net(seed)
+        cnet = compile_network([torch.from_numpy(w) for w in wf], [torch.from_numpy(b) for b in bf], scales, zeros, r,
+                               pe_add_bits=pe_add_bit)
+        net = Int8Net(cnet)
+        for i in range(5):
+            layouts.setdefault(net.layer_layout(i), []).append("seed%d/L%d" % (seed, i))
+    for case in ALL_CASES:
+        g = load_golden(case)
+        cnet = compile_network([torch.from_numpy(w) for w in g.wf], [torch.from_numpy(b) for b in g.bf], g.scales, g.zeros, g.r,
+                               pe_add_bits=g.pe_add_bit)
+        net = Int8Net(cnet)
+        for i in range(5):
+            layouts.setdefault(net.layer_layout(i), []).append("%s/L%d" % (case, i))
+    print({k: len(v) for k, v in layouts.items()}, {k: v[:2] for k, v in layouts.items()})
+    for want in ("ns1", "spare", "ns2", "ns4", "generic"):
+        assert want in layouts, "no network of the test set selects the %s layout: %s" % (want, {k: len(v) for k, v in layouts.items()})
