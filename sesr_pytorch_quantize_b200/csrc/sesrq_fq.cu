@@ -481,6 +481,7 @@ int sesrq_fq_forward_batch(const SesrqFq* fq, const float* d_x, int B, int H, in
       fa.mm_stride = MM_STRIDE;
       fa.relu = D.relu[i];
       fa.cout = L.c.cout;
+      fa.one = 1.0f;
       int rc = launch_conv_umma_fq(L, act, fa, nb, H, W, st);
       if (rc) return rc;
     }

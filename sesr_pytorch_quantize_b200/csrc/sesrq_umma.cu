@@ -98,9 +98,11 @@ __device__ __forceinline__ void epilogue_half_fq_fast(const FqArgs& fa, const fl
                                                       const int h, const int (&a4)[4][8], float (&o)[16]) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    // NOTE: the PE sums are scalar adds on purpose.  ptxas contracts `mul.rn.f32x2` feeding `add.rn.f32x2` into one
-    // FFMA2 (seen in the SASS: a single rounding, not the reference's two); the scalar add.rn.f32 is never fused.
+    // NOTE: ptxas contracts `mul.rn.f32x2` feeding `add.rn.f32x2` into one FFMA2 (seen in the SASS: a single rounding,
+    // not the reference's two), and it also folds an FMA with a -0.0 addend back into that pattern.  The PE sum is
+    // therefore written as an FMA with a multiplier 1.0 that only the host knows, RN(y * 1 + s) = RN(y + s).
     float2 s = make_float2(0.f, 0.f);
+    const float2 one2 = make_float2(fa.one, fa.one);      // 1.0 as a run-time kernel parameter: ptxas cannot turn the FMA back into an add
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const float2 a = f2_add(make_float2(__int_as_float(a4[p][2 * kk]), __int_as_float(a4[p][2 * kk + 1])), -MAGIC_F);
@@ -109,8 +111,7 @@ __device__ __forceinline__ void epilogue_half_fq_fast(const FqArgs& fa, const fl
         yp.x = fminf(fmaxf(yp.x, cl.x), cl.y);                                               // :333
         yp.y = fminf(fmaxf(yp.y, cl.x), cl.y);
       }
-      s.x = __fadd_rn(s.x, yp.x);                                                            // :386 (first add: 0 + y_0)
-      s.y = __fadd_rn(s.y, yp.y);
+      s = f2_fma3(yp, one2, s);                                                              // :386 (first add: 0 + y_0)
     }
     if (CLAMP) {
       s.x = fminf(fmaxf(s.x, cl.z), cl.w);                                                   // :434
