@@ -462,6 +462,42 @@ __device__ __forceinline__ void mma_issue_band(const int bw, const int lane, con
   constexpr int GPB = TB / RG;
   const int rows = min(TB, nblk - bw * TB);                  // output rows of this band that exist (may be <= 0)
   const uint32_t slot0 = ring.base + (uint32_t)(bw * TB);
+  // ---- NS = 4 (one row per group, the whole accumulator ring is ONE tile): waiting for all 8 slots of the tile before the
+  // first MMA would serialise this tile's MMAs behind the previous tile's whole epilogue.  Wait two slots at a time, right
+  // before the source rows that touch them first (source row r touches the output rows <= r), so that the first rows of
+  // a tile are issued while the epilogue is still draining the last rows of the previous one. ----
+  if (RG == 1 && rows == TB) {
+    const uint32_t d_band = tmem_base + slot0 * NCOLS;
+    const uint32_t a_band_lo = (a_tile + (uint32_t)(bw * TB * ROW_UNITS)) | (a_lbo << 16);
+    const uint32_t Gb = Gt + (uint32_t)(bw * GPB);
+#pragma unroll
+    for (int q = 0; q < TB / 2; ++q) {
+      {
+        const uint32_t bar = acc_empty_addr + (slot0 + (uint32_t)(2 * q + (lane & 1))) * 8u;
+        uint32_t ok;
+        do {
+          ok = 1u;
+          if (lane < 2)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}\n"
+                : "=r"(ok) : "r"(bar), "r"(ring.par), "r"(MBAR_SUSPEND_NS) : "memory");
+        } while (!__all_sync(0xffffffffu, ok != 0u));
+        tc_fence_after();
+      }
+      if (elect_one()) {
+#pragma unroll
+        for (int r = 2 * q; r < (q == TB / 2 - 1 ? TB + KS - 1 : 2 * q + 2); ++r) {
+          issue_row<KS, NS, NPAIR, ROW_UNITS, PAIR_STEP>(r, TB, d_band, a_band_lo, w_units, idesc0);
+          const int o_done = r - (KS - 1);
+          if (o_done >= 0) umma_commit_addr(acc_full_addr + ((Gb + (uint32_t)o_done) % NSLOT) * 8u);
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
   // ---- all groups of the band pre-loaded?  (lane l < GPB <-> group l of the band; acc_empty is per group of RG slots) ----
   {
     const int gl = lane & (GPB - 1);

@@ -177,7 +177,7 @@ __device__ __forceinline__ uint32_t pack4_sat_s8(int a, int b, int c, int d) {
 constexpr int UMMA_M = 128;
 constexpr int TMEM_COLS = 512;
 #ifndef SESRQ_FQ_EPI_WARPS
-#define SESRQ_FQ_EPI_WARPS 8            // epilogue warps of the exe_mode 0 kernels
+#define SESRQ_FQ_EPI_WARPS 12           // epilogue warps of the exe_mode 0 kernels (calibration leg: 8 warps 4.90 ms, 12: 4.78 ms, 16: 5.1 ms -- spills)
 #endif
 constexpr int CTRL_WARPS = 4;            // warp 0: TMA producer; warps 1-3: MMA issuers (keeps epilogue warp % 4 == lane quarter)
 constexpr int MAX_STAGES = 4;
