@@ -81,6 +81,25 @@ def test_segments_and_many_strips_vs_c_oracle(B, H, W):
     assert np.array_equal(y1.cpu().numpy(), y_ref)
 
 
+@pytest.mark.parametrize("case,B,H,W", [
+    ("x2_fixture", 16, 1080, 1920),        # the bench step (BASELINE config 5)
+    ("x4_fixture", 64, 540, 960),          # config 3 at its full batch
+    ("nrdm_fixture", 512, 80, 960),        # config 4 at its largest batch
+])
+def test_fused_equals_per_layer_at_baseline_sizes(case, B, H, W):
+    """Size-independent property at BASELINE.json's full sizes: the fused pair and the per-layer path give the same bytes."""
+    g, fused, plain = pair(case)
+    gen = torch.Generator().manual_seed(B + H)
+    x = torch.rand(B, g.wf[0].shape[1], H, W, generator=gen).cuda()
+    q1, y1 = fused(x)
+    h1 = (int(q1.view(torch.uint8).to(torch.int64).sum()), float(y1.double().sum()))
+    assert torch.equal(q1, plain(x, want_y=False)[0])
+    del q1
+    y0 = plain(x, want_q5=False)[1]
+    assert torch.equal(y1, y0)
+    assert h1[0] > 0
+
+
 def test_extreme_inputs_and_determinism():
     g, fused, plain = pair("x2_fixture")
     for fill in (0.0, 1.0, -3.0, 1e6):
