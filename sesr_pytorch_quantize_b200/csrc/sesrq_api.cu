@@ -305,7 +305,7 @@ int sesrq_net_layer_info(const SesrqNet* net, int layer, int32_t* impl, int32_t*
 }
 
 int sesrq_net_set_fusion(SesrqNet* net, int enable) {
-  if (!net) return -SESRQ_EINVAL;
+  if (!net) return SESRQ_EINVAL;
   const int prev = net->fuse12 ? 1 : 0;
   net->fuse12 = enable != 0;
   return prev;

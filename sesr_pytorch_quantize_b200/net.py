@@ -95,7 +95,7 @@ class Int8Net:
         so read_activation(2) needs fusion off).  Returns the previous setting."""
         prev = self.lib.sesrq_net_set_fusion(self._h, int(bool(enable)))
         if prev < 0:
-            _lib.check(-prev, "sesrq_net_set_fusion")
+            _lib.check(prev, "sesrq_net_set_fusion")
         return bool(prev)
 
     @property

@@ -37,6 +37,18 @@ def test_load_and_error_strings():
     assert isinstance(lib.sesrq_launch_count(), int)
 
 
+def test_handle_entry_points_reject_a_null_handle():
+    """Error behaviour of the entry points that take a net handle: a negative SESRQ_E* code (never a crash, never a
+    positive value that could be mistaken for a result)."""
+    lib = _lib.load_library()
+    assert lib.sesrq_net_set_fusion(None, 1) == -1            # SESRQ_EINVAL
+    assert lib.sesrq_net_layer_layout(None, 0) == -1
+    assert lib.sesrq_net_fused_layers(None) == 0
+    assert lib.sesrq_net_layer_info(None, 0, None, None) == -1
+    assert lib.sesrq_ws_bytes(None, 1, 8, 8) == 0
+    assert lib.sesrq_net_profile_enable(None, 1) == -1
+
+
 def test_struct_layout_matches_header():
     # sizes the C compiler produces for the two descriptor structs (checked with a tiny C probe)
     import subprocess, tempfile, textwrap
