@@ -14,7 +14,7 @@ shape = tuple(int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (1, 40, 3
 g = load_golden(case)
 cnet = compile_network([torch.from_numpy(w) for w in g.wf], [torch.from_numpy(b) for b in g.bf], g.scales, g.zeros, g.r,
                        pe_add_bits=g.pe_add_bit)
-net = Int8Net(cnet, impl=IMPL_AUTO)
+net = Int8Net(cnet, impl=IMPL_AUTO, fuse=False)      # layer by layer: every intermediate domain is read back
 print("layer impl/pe_exact:", [net.layer_info(i) for i in range(5)], flush=True)
 B, H, W = shape
 x = torch.rand(B, g.wf[0].shape[1], H, W, generator=torch.Generator().manual_seed(5))
