@@ -60,6 +60,7 @@ struct SesrqNet {
   std::vector<int8_t> h_w[SESRQ_NUM_LAYERS];
   bool need_rc = false;       // z_1 != -128: shortcut codes differ from q_1 (quan_func.py:250 vs :280)
   bool need_a0 = false;       // layer 0 runs on the generic path -> separate input-quantise pass
+  int alternate = 1;          // 1: consecutive launches walk their tiles in opposite directions (SESRQ_ALTERNATE=0 disables)
   bool fuse12 = true;         // layers 1 + 2 in one launch (sesrq_chain.cu); domain 2 is then never materialised
   int device = 0;
   size_t chunk_bytes = (size_t)2048 << 20;   // activation workspace per pass (SESRQ_CHUNK_MB, read at create)
@@ -183,6 +184,7 @@ int sesrq_net_create(const SesrqNetDesc* d, SesrqNet** out_net) {
   }
   if (const char* e = getenv("SESRQ_HOST_CHUNK")) net->host_chunk = std::max(0, atoi(e));
   if (const char* e = getenv("SESRQ_FUSE")) net->fuse12 = atoi(e) != 0;
+  if (const char* e = getenv("SESRQ_ALTERNATE")) net->alternate = atoi(e) != 0 ? 1 : 0;
   int zs[SESRQ_NUM_DOMAINS];
   for (int i = 0; i < SESRQ_NUM_LAYERS; ++i) zs[i] = d->layers[i].z_in;
   zs[5] = d->z_out;
@@ -351,10 +353,11 @@ int sesrq_net_forward_i8(const SesrqNet* net, const float* d_x, int B, int H, in
     float* y = d_y ? d_y + (size_t)b0 * cout * hw : nullptr;     // Cout/r^2 * rH * rW == Cout * H * W
     (void)r;
     int rc;
+    int rev = 0;                                  // tile order alternates from launch to launch (L2 reuse, launch_conv_umma)
     // layer 0
     if (net->layers[0].impl == SESRQ_IMPL_UMMA) {
       ProfScope ps(net, st, 0);
-      rc = launch_conv_umma(net->layers[0], x, nullptr, nullptr, A[1], nullptr, nullptr, nb, H, W, st);
+      rc = launch_conv_umma(net->layers[0], x, nullptr, nullptr, A[1], nullptr, nullptr, nb, H, W, st, rev);
     } else {
       {
         ProfScope ps(net, st, SESRQ_NUM_LAYERS);
@@ -370,7 +373,7 @@ int sesrq_net_forward_i8(const SesrqNet* net, const float* d_x, int B, int H, in
       const LayerDev& L = net->layers[i];
       if (i == 1 && net->fuse12 && chain2_supported(net->layers[1], net->layers[2])) {
         ProfScope ps(net, st, 1);                 // both layers in one launch, A[2] is skipped
-        rc = launch_conv_chain2(net->layers[1], net->layers[2], A[1], A[3], nb, H, W, st);
+        rc = launch_conv_chain2(net->layers[1], net->layers[2], A[1], A[3], nb, H, W, st, rev ^= net->alternate);
         if (rc) return rc;
         i = 2;
         continue;
@@ -379,7 +382,7 @@ int sesrq_net_forward_i8(const SesrqNet* net, const float* d_x, int B, int H, in
       uint8_t* out = (i < 4) ? A[i + 1] : nullptr;
       ProfScope ps(net, st, i);
       if (L.impl == SESRQ_IMPL_UMMA)
-        rc = launch_conv_umma(L, nullptr, A[i], sc, out, i == 4 ? q5 : nullptr, i == 4 ? y : nullptr, nb, H, W, st);
+        rc = launch_conv_umma(L, nullptr, A[i], sc, out, i == 4 ? q5 : nullptr, i == 4 ? y : nullptr, nb, H, W, st, rev ^= net->alternate);
       else
         rc = launch_conv_generic(L, A[i], sc, out, nullptr, i == 4 ? q5 : nullptr, i == 4 ? y : nullptr, nb, H, W, st);
       if (rc) return rc;

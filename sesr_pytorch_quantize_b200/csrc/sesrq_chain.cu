@@ -58,6 +58,7 @@ constexpr uint32_t CH_WL_BYTES = CH_W_BYTES + CH_C_BYTES;   // shared-memory wei
 
 struct ChainGeom {
   int32_t B, H, W, TW, tiles_x, nseg, SH, num_strips;
+  int32_t rev;                                          // 1: strips are processed last to first
   uint32_t idesc;
 };
 
@@ -66,6 +67,7 @@ struct ChainStrip {
 };
 __device__ __forceinline__ ChainStrip chain_strip(const ChainGeom& G, int s) {
   ChainStrip t;
+  if (G.rev) s = G.num_strips - 1 - s;
   const int cx = s % G.tiles_x;
   const int q = s / G.tiles_x;
   const int seg = q % G.nseg;
@@ -636,7 +638,7 @@ bool chain2_supported(const LayerDev& A, const LayerDev& B) {
 }
 
 int launch_conv_chain2(const LayerDev& A, const LayerDev& Bl, const uint8_t* d_in, uint8_t* d_out, int B, int H, int W,
-                       cudaStream_t st) {
+                       cudaStream_t st, int rev) {
   if (!chain2_supported(A, Bl)) return SESRQ_EUNSUPPORTED;
   if (!d_in || !d_out) return SESRQ_EINVAL;
   EncodeTiledFn encode = get_encode_fn();
@@ -667,6 +669,7 @@ int launch_conv_chain2(const LayerDev& A, const LayerDev& Bl, const uint8_t* d_i
   G.nseg = best_nseg;
   G.SH = cdiv(H, G.nseg);
   G.num_strips = (int)(cols * G.nseg);
+  G.rev = rev ? 1 : 0;
   G.idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(UMMA_M >> 4) << 24);
 
   CUtensorMap tmap;

@@ -51,12 +51,12 @@ bool umma_supported(const LayerConst& c);
 int umma_prepare_layer(LayerDev& L, const int8_t* h_w);                 // builds d_wumma
 int launch_conv_umma(const LayerDev& L, const float* d_x /*layer 0*/, const uint8_t* d_in,
                      const uint8_t* d_shortcut, uint8_t* d_out, int8_t* d_q5, float* d_y, int B, int H,
-                     int W, cudaStream_t st);
+                     int W, cudaStream_t st, int rev = 0);   // rev: walk the tiles last to first
 
 // ---- two 3x3 layers per launch: sesrq_chain.cu ---------------------------------------------------
 bool chain2_supported(const LayerDev& A, const LayerDev& B);            // both plain 3x3, 16 -> 16 channels, tcgen05 layout NS = 1
 int launch_conv_chain2(const LayerDev& A, const LayerDev& B, const uint8_t* d_in, uint8_t* d_out, int Bn, int H, int W,
-                       cudaStream_t st);
+                       cudaStream_t st, int rev = 0);
 
 // exe_mode 0 conv on the tcgen05 path (4 PE-masked accumulator sets, float-domain epilogue): L.c.epi == EPI_FQ
 int launch_conv_umma_fq(const LayerDev& L, const uint8_t* d_in, const FqArgs& fa, int B, int H, int W, cudaStream_t st);

@@ -319,8 +319,9 @@ __device__ __forceinline__ void epilogue_warps(const UmmaParams& P, const int ew
   RingPos ring;
   uint32_t G0 = 0;                              // groups of all earlier tiles
   for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ring.advance((uint32_t)P.TH, nring)) {
-    const int b = t / tiles_per_frame;
-    const int r = t - b * tiles_per_frame;
+    const int tt = P.dbg < 0 ? P.num_tiles - 1 - t : t;      // tile order (launch_conv_umma: alternates from layer to layer)
+    const int b = tt / tiles_per_frame;
+    const int r = tt - b * tiles_per_frame;
     const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
     const int y0 = ty * P.TH, gx = tx * P.TW + ox;
     const int nblk = min(P.TH, P.H - y0);
@@ -603,9 +604,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       int st = 0, sst = 0;
       uint32_t ph = 0, sph = 0;              // phase parity of the current pass over the stage rings
       for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+        const int tt = P.dbg < 0 ? P.num_tiles - 1 - t : t;      // tile order (launch_conv_umma: alternates from layer to layer)
         mbar_wait(&tile_empty[st], ph ^ 1);
-        const int b = t / tiles_per_frame;
-        const int r = t - b * tiles_per_frame;
+        const int b = tt / tiles_per_frame;
+        const int r = tt - b * tiles_per_frame;
         const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
         mbar_arrive_expect_tx(&tile_full[st], P.box_bytes);
         tma_load_3d(tile0 + (size_t)st * P.stage_bytes, &tmap, (tx * P.TW - P.pad) * 2, ty * P.TH - P.pad, b, &tile_full[st]);
@@ -634,7 +636,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       uint32_t Gt = 0;
       RingPos ring;
       for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
-        const int r = t % tiles_per_frame;
+        const int tt = P.dbg < 0 ? P.num_tiles - 1 - t : t;      // tile order (launch_conv_umma: alternates from layer to layer)
+        const int r = tt % tiles_per_frame;
         const int nblk = min(P.TH, P.H - (r / P.tiles_x) * P.TH);     // rows of this tile that exist
         mbar_wait(&tile_full[st], ph);
         tc_fence_after();
@@ -766,12 +769,13 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       int xs = 0;
       uint32_t xph = 0;
       for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+        const int tt = P.dbg < 0 ? P.num_tiles - 1 - t : t;      // tile order (launch_conv_umma: alternates from layer to layer)
 #ifdef SESRQ_DEBUG_KNOBS
         if (P.dbg & 512) break;
 #endif
         mbar_wait(&x_empty[xs], xph ^ 1);
-        const int b = t / tiles_per_frame;
-        const int r = t - b * tiles_per_frame;
+        const int b = tt / tiles_per_frame;
+        const int r = tt - b * tiles_per_frame;
         const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
         mbar_arrive_expect_tx(&x_full[xs], (uint32_t)(CIN * (P.TH + 2 * PAD) * L0_XP * 4));
         tma_load_4d(region2 + (size_t)xs * P.xstage_bytes, &xmap, (tx * P.TW - PAD) & ~3, ty * P.TH - PAD, 0, b, &x_full[xs]);
@@ -791,7 +795,8 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       uint32_t Gt = 0;
       RingPos ring;
       for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
-        const int r = t % tiles_per_frame;
+        const int tt = P.dbg < 0 ? P.num_tiles - 1 - t : t;      // tile order (launch_conv_umma: alternates from layer to layer)
+        const int r = tt % tiles_per_frame;
         const int nblk = min(P.TH, P.H - (r / P.tiles_x) * P.TH);
         mbar_wait(&e_full[st], ph);
         tc_fence_after();
@@ -830,7 +835,8 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       int xs = 0;
       uint32_t xph = 0;
       for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
-        const int r = t % tiles_per_frame;
+        const int tt = P.dbg < 0 ? P.num_tiles - 1 - t : t;      // tile order (launch_conv_umma: alternates from layer to layer)
+        const int r = tt % tiles_per_frame;
 #ifdef SESRQ_DEBUG_KNOBS
         const int rows = (P.dbg & 256) ? 0 : min(P.TH, P.H - (r / P.tiles_x) * P.TH) + 2 * PAD;
 #else
@@ -903,8 +909,9 @@ conv_umma_l0_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       }
     } else
     for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
-      const int b = t / tiles_per_frame;
-      const int r = t - b * tiles_per_frame;
+      const int tt = P.dbg < 0 ? P.num_tiles - 1 - t : t;      // tile order (launch_conv_umma: alternates from layer to layer)
+      const int b = tt / tiles_per_frame;
+      const int r = tt - b * tiles_per_frame;
       const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
       const int y0 = ty * P.TH - PAD, x0 = tx * P.TW - PAD;
       const int rows = min(P.TH, P.H - ty * P.TH) + 2 * PAD;
@@ -1299,7 +1306,7 @@ static int launch_l0_one(const CUtensorMap& xmap, const UmmaParams& P, const Lay
   return SESRQ_OK;
 }
 
-static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_out, int B, int H, int W, cudaStream_t st) {
+static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_out, int B, int H, int W, cudaStream_t st, int rev) {
   const LayerConst& c = L.c;
   if (!d_x || !d_out) return SESRQ_EINVAL;
   const int pad = c.pad, ns = L.umma_n / 16, N = L.umma_n;
@@ -1370,7 +1377,7 @@ static int launch_conv_umma_l0(const LayerDev& L, const float* d_x, uint8_t* d_o
   for (int ci = 0; ci < c.cin; ++ci) P.pad_word |= (uint32_t)c.pad_byte << (8 * ci);
   P.in_scale = c.in_scale;
   P.in_zero = c.in_zero;
-  P.dbg = tuning().dbg;
+  P.dbg = tuning().dbg | (rev ? UMMA_REV : 0);
   const int grid = std::min(P.num_tiles, sms);
 #define SESRQ_L0_NS(KS_, CIN_)                                                                              \
   do {                                                                                                      \
@@ -1479,14 +1486,17 @@ static int plan_conv_launch(const LayerDev& L, const uint8_t* d_in, int B, int H
 }
 
 int launch_conv_umma(const LayerDev& L, const float* d_x, const uint8_t* d_in, const uint8_t* d_shortcut,
-                     uint8_t* d_out, int8_t* d_q5, float* d_y, int B, int H, int W, cudaStream_t st) {
+                     uint8_t* d_out, int8_t* d_q5, float* d_y, int B, int H, int W, cudaStream_t st, int rev) {
   const LayerConst& c = L.c;
-  if (is_l0_layout(c)) return launch_conv_umma_l0(L, d_x, d_out, B, H, W, st);
+  if (is_l0_layout(c)) return launch_conv_umma_l0(L, d_x, d_out, B, H, W, st, rev);
   UmmaParams P;
   CUtensorMap tmap, smap;
   int grid = 0;
   size_t smem = 0;
   if (int rc = plan_conv_launch(L, d_in, B, H, W, P, tmap, grid, smem, d_shortcut, &smap)) return rc;
+  // Tile order.  A layer finishes with its last tiles' output still in the 126 MB L2; its consumer starts with those tiles
+  // when it walks the tiles in the opposite direction (sesrq_net_forward_i8 alternates `rev` from launch to launch).
+  if (rev) P.dbg |= UMMA_REV;
   const int ns = L.umma_n / 16;
   const CUtensorMap* sp = P.sc_stages > 0 ? &smap : nullptr;
   if (c.k == 3) return launch_ns<3>(ns, c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, sp);

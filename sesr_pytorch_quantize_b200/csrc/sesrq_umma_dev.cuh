@@ -257,7 +257,9 @@ struct UmmaParams {
   float res_mf, res_nbias, z_res;        // EPI_RESIDUAL: Mres * 2^-nres, -12582912 * res_mf, z_4
   float s_out, out_off;                  // EPI_FINAL: f32(s_5), -(12582912 + z_5)
   int32_t relu, cout;
-  int32_t dbg;                           // SESRQ_UMMA_DBG bit mask (pipeline experiments only; results are wrong when set)
+  int32_t dbg;                           // bits 0..30: SESRQ_UMMA_DBG mask (pipeline experiments only; results are wrong when set);
+                                         // bit 31 (UMMA_REV): walk the tiles last to first (launch_conv_umma).  It lives here because
+                                         // growing this struct by one word took conv_chain2_kernel from 74 to 96 registers + spills
   // geometry
   int32_t B, H, W, TH, TW, tiles_x, tiles_y, num_tiles, pad;
   uint32_t box_bytes, stage_bytes, w_bytes;
@@ -274,6 +276,8 @@ struct UmmaParams {
   int32_t xstages;                       // fp32 tile buffers in flight (2..L0_XSTAGES)
   uint32_t xstage_bytes;                 // one fp32 tile buffer: cin planes of (TH + 2 pad) rows x L0_XP floats
 };
+
+constexpr int32_t UMMA_REV = (int32_t)0x80000000;
 
 __device__ __forceinline__ void st_y2(float* p, float2 v) {
   if (SESRQ_X_STCS >= 1) __stcs(reinterpret_cast<float2*>(p), v);
