@@ -1432,7 +1432,8 @@ static int plan_conv_launch(const LayerDev& L, const uint8_t* d_in, int B, int H
   // slack: the last row's rightmost K chunk reaches 2*pad + 1 pixels past the row
   // measured: 16-channel layers are fastest with 2 bands (TH = 16: the 32-slot ring then holds two tiles; 1080p x2 3x3
   // 0.178 vs 0.185 ms with 3 bands); the 16-output x4 final layer with 3 (540x960: 0.909 vs 0.955 ms)
-  int prefer = (c.epi == EPI_FINAL && c.r_shuffle == 4) ? 3 : 2;
+  // (round 2: the 3-output NRDM final layer, 512 frames of 80x960: 1.254 / 1.170 / 1.133 ms per step with 1 / 2 / 3 bands)
+  int prefer = (c.epi == EPI_FINAL && (c.r_shuffle == 4 || c.cout <= 4)) ? 3 : 2;
   if (c.epi == EPI_FINAL && tuning().nbw_final > 0) prefer = tuning().nbw_final;   // tuning experiments
   const TilePlan tp = choose_tiling(H, ns, prefer, pad, (size_t)UMMA_M * 16, (size_t)(2 * pad + 1) * 16, 0, fixed);
   if (tp.stages < 2) return SESRQ_EUNSUPPORTED;
