@@ -1226,6 +1226,19 @@ template <int KS>
 static int launch_ns(int ns, const LayerConst& c, const CUtensorMap& tmap, const UmmaParams& P, const LayerDev& L,
                      const uint8_t* d_shortcut, uint8_t* d_out, int8_t* d_q5, float* d_y, int grid, size_t smem,
                      cudaStream_t st, const CUtensorMap* smap) {
+  // x2 final layer (PixelShuffle(2)) with the fp32 output materialised: 8 epilogue warps instead of 16.  Fewer warps = fewer
+  // concurrent write streams per SM; measured on 16 x 1080p (ms, 4 / 8 / 12 / 16 / 20 warps): y only 0.416 / 0.375 / 0.409 /
+  // 0.390 / 0.375, both outputs 0.731 / 0.525 / 0.578 / 0.607 / 0.533, q5 only 0.707 / 0.449 / - / 0.345 / 0.384 (so q5-only
+  // keeps 16).  The x4 and NRDM final layers show no gain (1.176 vs 1.176 ms, 1.125 vs 1.139 ms per step) and keep 16.
+  if (ns == 1 && c.epi == EPI_FINAL && c.r_shuffle == 2 && d_y) {
+    const FqArgs nofq{};
+    if (c.cout == 12) {
+      if (d_q5) return launch_one<KS, 1, EPI_FINAL, 2, 12, 0, false, 8>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, nofq, smap);
+      return launch_one<KS, 1, EPI_FINAL, 2, 12, 2, false, 8>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, nofq, smap);
+    }
+    if (d_q5) return launch_one<KS, 1, EPI_FINAL, 2, 0, 0, false, 8>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, nofq, smap);
+    return launch_one<KS, 1, EPI_FINAL, 2, 0, 2, false, 8>(tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, nofq, smap);
+  }
   if (ns == 1) return launch_epi<KS, 1, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, smap);
   if (ns == 2) return launch_epi<KS, 2, 16>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, smap);
   return launch_epi<KS, 4, 8>(c, tmap, P, L, d_shortcut, d_out, d_q5, d_y, grid, smem, st, smap);
