@@ -230,7 +230,7 @@ constexpr bool X_ROWARRIVE = false;
 // The 4 warps of a warpgroup meet at a named barrier before every row, so that their stores to the same output rows
 // (q5: 4 x 32 misaligned bytes of one plane row = whole sectors only together; y: 4 x 256 B of one HR row) leave the SM
 // within a few hundred cycles of each other.  Measured on 16 x 1080p: final layer both 0.745 -> 0.626 ms, y only
-// 0.435 -> 0.411 (profiles/r2_final_layer.txt); 0 = off, 1 = final layer (default), 2 = every layer.
+// 0.435 -> 0.411 (profiles/final_layer_study_r2.txt); 0 = off, 1 = final layer (default), 2 = every layer.
 #ifndef SESRQ_X_ROWSYNC
 #define SESRQ_X_ROWSYNC 1
 #endif
