@@ -37,8 +37,14 @@ constexpr int CH_HALF = 8;                              // rows per issue step /
 constexpr int CH_HPB = CH_BLK / CH_HALF;                // halves per block
 constexpr int CH_RG = 4;                                // rows per accumulator group (completion / re-arm signalling)
 constexpr int CH_GPB = CH_BLK / CH_RG;                  // accumulator groups per block
-constexpr int CH_IN_BLOCKS = 3;                         // input ring: 3 x 32 KB
-constexpr int CH_MID_BLOCKS = 2;                        // mid ring:   2 x 32 KB
+#ifndef SESRQ_CHAIN_IN_BLOCKS
+#define SESRQ_CHAIN_IN_BLOCKS 3
+#endif
+#ifndef SESRQ_CHAIN_MID_BLOCKS
+#define SESRQ_CHAIN_MID_BLOCKS 2
+#endif
+constexpr int CH_IN_BLOCKS = SESRQ_CHAIN_IN_BLOCKS;      // input ring: 3 x 32 KB
+constexpr int CH_MID_BLOCKS = SESRQ_CHAIN_MID_BLOCKS;    // mid ring:   2 x 32 KB
 constexpr uint32_t CH_ROW_BYTES = UMMA_M * 16;          // one 128-pixel row of NHWC16
 constexpr uint32_t CH_BLK_BYTES = CH_BLK * CH_ROW_BYTES;
 constexpr int CH_EPI_WARPS = 8;                         // per layer: two warpgroups, each takes 2 rows of every 4-row group
