@@ -231,7 +231,9 @@ __device__ __forceinline__ void epilogue_group(const UmmaParams& P, const int cn
       else if (valid && i < cnt) sc[i] = __ldg(sc_row + (long long)i * P.W);
     }
   }
-  constexpr bool PIPE = !(X_NOPIPE && EPI == EPI_FINAL);
+  // software pipelining of the TMEM loads (next row's load in flight during this row's arithmetic).  The x2 last layer
+  // writing only y (8 epilogue warps) is faster WITHOUT it: 0.378 -> 0.367 ms (both outputs: 0.523 -> 0.528, so it keeps it)
+  constexpr bool PIPE = !(EPI == EPI_FINAL && (X_NOPIPE || (OUTM == 2 && RS == 2)));
   constexpr bool BRANCH = X_BRANCH && EPI == EPI_FINAL;
   int acc[PIPE ? 2 : 1][NS][16];
   if (PIPE) slot_load<NS>(taddr0, acc[0]);
