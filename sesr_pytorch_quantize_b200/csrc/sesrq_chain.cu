@@ -9,9 +9,10 @@
 //
 //   TMA (warp 0)        16-row blocks of the NHWC16 input, 128 pixels wide (2 halo columns / rows each side, zero-filled
 //                       outside the frame = code -128 = the reference's pad value, quan_func.py:351-352) -> input ring
-//   issuer A (warp 1)   per input row r two tcgen05.mma.kind::i8 (tap pairs) with N = 48: the row contributes to the
-//                       output rows r-2 .. r, whose accumulators are consecutive 16-column TMEM slots (the vertical taps
-//                       are batched into N exactly like sesrq_umma.cu's issue_row); slot ring of 16 rows
+//   issuer A (warp 1)   tcgen05.mma.kind::i8 with the vertical taps batched into N (as in sesrq_umma.cu's issue_row): source row r
+//                       contributes to the output rows r-2 .. r, whose accumulators are consecutive 16-column TMEM slots
+//                       (slot ring of 16 rows).  Per PAIR of source rows three MMAs: taps dx = 0, 1 of each row (N = 48)
+//                       and tap dx = 2 of both rows in one instruction (N = 64, A descriptor LBO = one row)
 //   epilogue A          8 warps: tcgen05.ld, exact requantisation (epilogue_pixel), codes of out-of-frame
 //   (warps 4-11)        positions forced to byte 0 (they are the NEXT layer's zero padding), 16 B per pixel st.shared into
 //                       the mid ring (32 rows), fence.proxy.async, mbarrier
@@ -23,9 +24,12 @@
 // X < 126); layer-B output index X <-> x0 + X (valid for X < 124 = the strip width).  Input row r <-> frame row
 // ys - 2 + r; layer-A output row o <-> ys - 1 + o (SH + 2 rows); layer-B output row o <-> ys + o.
 //
-// Synchronisation: every ring is cut into groups of 8 rows with one (full, empty) mbarrier pair per group position;
-// strips are padded to whole 16-row blocks with PHANTOM groups that travel through the same barriers without work, so
-// that all barriers of a ring stay in the same phase and the parity is a function of the running block counter alone.
+// Synchronisation: the accumulator rings are cut into groups of 4 rows, the mid ring into groups of 8 rows, the input ring
+// into its 16-row TMA blocks, each with one (full, empty) mbarrier pair per group position; both warpgroups of a layer's
+// epilogue share every 4-row group (2 rows each).  Strips are padded to whole 16-row blocks with PHANTOM groups that travel
+// through the same barriers without work, so that all barriers of a ring stay in the same phase and the parity is a
+// function of the running block counter alone.  What bounds the kernel: DESIGN.md section 3.3 (shared-memory bandwidth of
+// the operand streams); experiments kept behind build switches: SESRQ_CHAIN_BANDS, SESRQ_CHAIN_IN_BLOCKS / _MID_BLOCKS.
 #include <algorithm>
 #include <cstring>
 #include "sesrq_umma_dev.cuh"
